@@ -1,0 +1,573 @@
+// HBM-bound kernels of the Gatys closure: layout converts, the Cin=3 first conv (forward and data-gradient),
+// 2x2 max-pool forward / scatter-backward with the reference's tie rule, content MSE, Gram finalisation.
+// All tensors are NHWC 16-bit planes (hi, lo) unless a name says nchw / f32. Each thread moves 16-byte vectors
+// along the channel axis (fully coalesced); reductions are two-level with a fixed order (no float atomics), so
+// results are run-to-run bit-identical (SURVEY 8d "Determinism").
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "conv_igemm.cuh"
+
+namespace ist {
+
+// hi/lo pair of packed 16-bit values -> two fp32 sums (exact: hi + lo has <= 22 significant bits)
+template <bool BF>
+__device__ __forceinline__ void unpack_sum(uint32_t h, uint32_t l, float& a, float& b) {
+    if (BF) {
+        a = bf_lo_f(h) + bf_lo_f(l);
+        b = bf_hi_f(h) + bf_hi_f(l);
+    } else {
+        a = h_lo_f(h) + h_lo_f(l);
+        b = h_hi_f(h) + h_hi_f(l);
+    }
+}
+template <bool BF>
+__device__ __forceinline__ void split_pack(float a, float b, uint32_t& h, uint32_t& l) {
+    if (BF) {
+        h = pack_bf2(a, b);
+        l = pack_bf2(a - bf_lo_f(h), b - bf_hi_f(h));
+    } else {
+        h = pack_h2(a, b);
+        l = pack_h2(a - h_lo_f(h), b - h_hi_f(h));
+    }
+}
+
+// Fixed-order block reduction (sum or max) over 256 threads; result valid in thread 0.
+template <bool MAX>
+__device__ __forceinline__ float block_reduce_256(float v, float* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float t = __shfl_down_sync(0xffffffffu, v, o);
+        v = MAX ? fmaxf(v, t) : v + t;
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = threadIdx.x < 8 ? sh[threadIdx.x] : (MAX ? 0.f : 0.f);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            float t = __shfl_down_sync(0xffffffffu, v, o);
+            v = MAX ? fmaxf(v, t) : v + t;
+        }
+    }
+    __syncthreads();
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Layout converts (used at the API boundary: reference tensors are fp32 NCHW, vgg.py:44-58)
+// ------------------------------------------------------------------------------------------------------------
+template <bool BF>
+__global__ void nchw_to_planes_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi,
+                                      uint16_t* __restrict__ lo, int NB, int C, int HW, float scale) {
+    // one thread per (frame, pixel, channel pair); channel fastest so plane stores coalesce
+    const size_t total = (size_t)NB * HW * (C >> 1);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int cp = (int)(i % (C >> 1));
+        const size_t np = i / (C >> 1);
+        const int pix = (int)(np % HW);
+        const int n = (int)(np / HW);
+        const float a = src[((size_t)n * C + 2 * cp) * HW + pix] * scale;
+        const float b = src[((size_t)n * C + 2 * cp + 1) * HW + pix] * scale;
+        uint32_t h, l;
+        split_pack<BF>(a, b, h, l);
+        reinterpret_cast<uint32_t*>(hi)[i] = h;
+        reinterpret_cast<uint32_t*>(lo)[i] = l;
+    }
+}
+template <bool BF>
+__global__ void planes_to_nchw_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
+                                      float* __restrict__ dst, int NB, int C, int HW, float inv_scale) {
+    // one thread per (frame, channel pair, pixel); pixel fastest so NCHW stores coalesce
+    const size_t total = (size_t)NB * HW * (C >> 1);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int pix = (int)(i % HW);
+        const size_t nc = i / HW;
+        const int cp = (int)(nc % (C >> 1));
+        const int n = (int)(nc / (C >> 1));
+        const size_t s = ((size_t)n * HW + pix) * (C >> 1) + cp;
+        float a, b;
+        unpack_sum<BF>(reinterpret_cast<const uint32_t*>(hi)[s], reinterpret_cast<const uint32_t*>(lo)[s], a, b);
+        dst[((size_t)n * C + 2 * cp) * HW + pix] = a * inv_scale;
+        dst[((size_t)n * C + 2 * cp + 1) * HW + pix] = b * inv_scale;
+    }
+}
+__global__ void nchw_to_nhwc_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int NB, int C, int HW) {
+    const size_t total = (size_t)NB * HW * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const size_t np = i / C;
+        const int pix = (int)(np % HW);
+        const int n = (int)(np / HW);
+        dst[i] = src[((size_t)n * C + c) * HW + pix];
+    }
+}
+__global__ void nhwc_to_nchw_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int NB, int C, int HW) {
+    const size_t total = (size_t)NB * HW * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int pix = (int)(i % HW);
+        const size_t nc = i / HW;
+        const int c = (int)(nc % C);
+        const int n = (int)(nc / C);
+        dst[i] = src[((size_t)n * HW + pix) * C + c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Weight repack: OIHW fp32 -> [tap][Cout][Cin] planes (forward, fp16, scaled) and [tap'][Cin][Cout] planes
+// (data-gradient, bf16, taps flipped): dX = conv(dY, flip(W)^T).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void weight_repack_kernel(const float* __restrict__ w, int Cout, int Cin, float scale_fwd,
+                                     uint16_t* __restrict__ f_hi, uint16_t* __restrict__ f_lo,
+                                     uint16_t* __restrict__ d_hi, uint16_t* __restrict__ d_lo) {
+    const size_t total = (size_t)Cout * Cin * 9;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % 9);
+        const size_t oc = i / 9;
+        const int ci = (int)(oc % Cin);
+        const int co = (int)(oc / Cin);
+        const float v = w[i];
+        {
+            const float s = v * scale_fwd;
+            const __half h = __float2half_rn(s);
+            const __half l = __float2half_rn(s - __half2float(h));
+            const size_t o = ((size_t)tap * Cout + co) * Cin + ci;
+            f_hi[o] = __half_as_ushort(h);
+            f_lo[o] = __half_as_ushort(l);
+        }
+        {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+            const size_t o = ((size_t)(8 - tap) * Cin + ci) * Cout + co;
+            d_hi[o] = __bfloat16_as_ushort(h);
+            d_lo[o] = __bfloat16_as_ushort(l);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// First conv (Cin = 3, K = 27): HBM-bound, exact fp32 on CUDA cores. x is the reference's fp32 NCHW image
+// (the L-BFGS vector); output = relu planes. Reference: vgg.py:52 for conv1_1.
+// ------------------------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(128)
+conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /*[COUT][3][3][3]*/,
+                      const float* __restrict__ bias, uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo,
+                      int NB, int H, int W, float out_scale) {
+    __shared__ __align__(16) float ws[27][COUT];
+    __shared__ float bs[COUT];
+    for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
+        const int co = i / 27, t = i % 27;      // w index = co*27 + (ci*9 + ky*3 + kx)
+        ws[t][co] = w[i];
+    }
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = bias[i];
+    __syncthreads();
+    const size_t HW = (size_t)H * W;
+    const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (gid >= (size_t)NB * HW) return;
+    const int n = (int)(gid / HW);
+    const int pix = (int)(gid % HW);
+    const int y = pix / W, xx = pix % W;
+    float in[27];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int yy = y + ky - 1, xq = xx + kx - 1;
+                in[ci * 9 + ky * 3 + kx] =
+                    (yy >= 0 && yy < H && xq >= 0 && xq < W) ? __ldg(x + ((size_t)n * 3 + ci) * HW + (size_t)yy * W + xq) : 0.f;
+            }
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+        const float xv = in[t];
+#pragma unroll
+        for (int c = 0; c < COUT; c += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&ws[t][c]);
+            acc[c] = fmaf(xv, w4.x, acc[c]);
+            acc[c + 1] = fmaf(xv, w4.y, acc[c + 1]);
+            acc[c + 2] = fmaf(xv, w4.z, acc[c + 2]);
+            acc[c + 3] = fmaf(xv, w4.w, acc[c + 3]);
+        }
+    }
+    uint4* dh = reinterpret_cast<uint4*>(out_hi + gid * COUT);
+    uint4* dl = reinterpret_cast<uint4*>(out_lo + gid * COUT);
+#pragma unroll
+    for (int c = 0; c < COUT; c += 8) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float a = fmaxf(acc[c + 2 * e] + bs[c + 2 * e], 0.f) * out_scale;
+            const float b = fmaxf(acc[c + 2 * e + 1] + bs[c + 2 * e + 1], 0.f) * out_scale;
+            split_pack<false>(a, b, h[e], l[e]);
+        }
+        dh[c >> 3] = make_uint4(h[0], h[1], h[2], h[3]);
+        dl[c >> 3] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+// Data-gradient of the first conv: dX[ci,y,x] = sum_{co,ky,kx} W[co,ci,ky,kx] * dY[co, y-ky+1, x-kx+1].
+// dY = bf16 planes already masked by relu1_1; output = fp32 NCHW image gradient (x.grad of utils.py:36).
+template <int COUT>
+__global__ void __launch_bounds__(128)
+conv_first_dgrad_kernel(const uint16_t* __restrict__ g_hi, const uint16_t* __restrict__ g_lo,
+                        const float* __restrict__ w /*[COUT][3][3][3]*/, float* __restrict__ grad, int NB, int H, int W) {
+    __shared__ float ws[9][COUT][3];
+    for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
+        const int co = i / 27, r = i % 27, ci = r / 9, tap = r % 9;
+        ws[tap][co][ci] = w[i];
+    }
+    __syncthreads();
+    const size_t HW = (size_t)H * W;
+    const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (gid >= (size_t)NB * HW) return;
+    const int n = (int)(gid / HW);
+    const int pix = (int)(gid % HW);
+    const int y = pix / W, xx = pix % W;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap % 3;
+        const int yy = y - ky + 1, xq = xx - kx + 1;
+        if (yy < 0 || yy >= H || xq < 0 || xq >= W) continue;
+        const size_t o = (((size_t)n * H + yy) * W + xq) * COUT;
+        const uint4* ph = reinterpret_cast<const uint4*>(g_hi + o);
+        const uint4* pl = reinterpret_cast<const uint4*>(g_lo + o);
+#pragma unroll
+        for (int q = 0; q < COUT / 8; ++q) {
+            const uint4 h = __ldg(ph + q), l = __ldg(pl + q);
+            const uint32_t uh[4] = {h.x, h.y, h.z, h.w}, ul[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float va, vb;
+                unpack_sum<true>(uh[e], ul[e], va, vb);
+                const int co = q * 8 + 2 * e;
+                a0 = fmaf(va, ws[tap][co][0], a0);
+                a1 = fmaf(va, ws[tap][co][1], a1);
+                a2 = fmaf(va, ws[tap][co][2], a2);
+                a0 = fmaf(vb, ws[tap][co + 1][0], a0);
+                a1 = fmaf(vb, ws[tap][co + 1][1], a1);
+                a2 = fmaf(vb, ws[tap][co + 1][2], a2);
+            }
+        }
+    }
+    grad[((size_t)n * 3 + 0) * HW + pix] = a0;
+    grad[((size_t)n * 3 + 1) * HW + pix] = a1;
+    grad[((size_t)n * 3 + 2) * HW + pix] = a2;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// MaxPool2d(2,2) forward (vgg.py:21-22,54): floor(H/2) x floor(W/2); first maximum in row-major window order
+// wins (strict >), matching ATen. One thread = one output pixel x 8 channels.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const uint16_t* __restrict__ in_hi, const uint16_t* __restrict__ in_lo,
+                                   uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, int NB, int H, int W,
+                                   int C) {
+    const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
+    const size_t total = (size_t)NB * Ho * Wo * C8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        size_t r = i / C8;
+        const int xo = (int)(r % Wo);
+        r /= Wo;
+        const int yo = (int)(r % Ho);
+        const int n = (int)(r / Ho);
+        uint32_t bh[4], bl[4];
+        float bv[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const size_t o = ((((size_t)n * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)) * C) / 8 + c8;
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(in_hi) + o);
+            const uint4 l = __ldg(reinterpret_cast<const uint4*>(in_lo) + o);
+            const uint32_t uh[4] = {h.x, h.y, h.z, h.w}, ul[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float a, b;
+                unpack_sum<false>(uh[e], ul[e], a, b);
+                if (k == 0) {
+                    bv[2 * e] = a; bv[2 * e + 1] = b; bh[e] = uh[e]; bl[e] = ul[e];
+                } else {
+                    if (a > bv[2 * e]) {
+                        bv[2 * e] = a;
+                        bh[e] = (bh[e] & 0xFFFF0000u) | (uh[e] & 0xFFFFu);
+                        bl[e] = (bl[e] & 0xFFFF0000u) | (ul[e] & 0xFFFFu);
+                    }
+                    if (b > bv[2 * e + 1]) {
+                        bv[2 * e + 1] = b;
+                        bh[e] = (bh[e] & 0xFFFFu) | (uh[e] & 0xFFFF0000u);
+                        bl[e] = (bl[e] & 0xFFFFu) | (ul[e] & 0xFFFF0000u);
+                    }
+                }
+            }
+        }
+        reinterpret_cast<uint4*>(out_hi)[i] = make_uint4(bh[0], bh[1], bh[2], bh[3]);
+        reinterpret_cast<uint4*>(out_lo)[i] = make_uint4(bl[0], bl[1], bl[2], bl[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Gradient routing at a ReLU output F (pre-pool resolution H x W):
+//   v(pos) = [pos == first-argmax of its 2x2 window ? g_pool(window) : 0]  (if g_pool != nullptr)
+//          + addend(pos) (if any) + content_coef * (F - T)(pos) (if any);  then v = F > 0 ? v : 0 (if mask)
+// Output: bf16 planes (the dY the next dgrad consumes) or fp32 NHWC (when a style seed is still to be added).
+// Covers autograd of max_pool2d + relu (threshold_backward) and the content MSE seed (main.py:36-37).
+// One thread = one 2x2 window (ceil grid so odd edges are written too) x 8 channels.
+// ------------------------------------------------------------------------------------------------------------
+struct RouteParams {
+    int NB, H, W, C;
+    const float* g_pool;        // fp32 NHWC [NB, H/2, W/2, C] or nullptr
+    const uint16_t* f_hi;       // fp16 planes of F (argmax + mask + content term)
+    const uint16_t* f_lo;
+    const float* addend;        // fp32 NHWC [NB,H,W,C] or nullptr
+    const uint16_t* t_hi;       // content target planes or nullptr
+    const uint16_t* t_lo;
+    float content_coef;
+    int apply_mask;
+    uint16_t* out_hi;           // bf16 planes, used when out_f32 == nullptr
+    uint16_t* out_lo;
+    float* out_f32;
+};
+
+__global__ void grad_route_kernel(const RouteParams p) {
+    const int Hc = (p.H + 1) >> 1, Wc = (p.W + 1) >> 1, C8 = p.C >> 3;
+    const int Ho = p.H >> 1, Wo = p.W >> 1;
+    const size_t total = (size_t)p.NB * Hc * Wc * C8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        size_t r = i / C8;
+        const int xo = (int)(r % Wc);
+        r /= Wc;
+        const int yo = (int)(r % Hc);
+        const int n = (int)(r / Hc);
+        const bool window = (p.g_pool != nullptr) && (yo < Ho) && (xo < Wo);
+        float g[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = 0.f;
+        if (window) {
+            const float4* gp = reinterpret_cast<const float4*>(p.g_pool + ((((size_t)n * Ho + yo) * Wo + xo) * p.C) + c8 * 8);
+            const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+            g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+        }
+        float fv[4][8];
+        bool inb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
+            inb[k] = (yy < p.H) && (xx < p.W);
+            if (inb[k]) {
+                const size_t o = ((((size_t)n * p.H + yy) * p.W + xx) * p.C) / 8 + c8;
+                const uint4 h = __ldg(reinterpret_cast<const uint4*>(p.f_hi) + o);
+                const uint4 l = __ldg(reinterpret_cast<const uint4*>(p.f_lo) + o);
+                const uint32_t uh[4] = {h.x, h.y, h.z, h.w}, ul[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) unpack_sum<false>(uh[e], ul[e], fv[k][2 * e], fv[k][2 * e + 1]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) fv[k][e] = 0.f;
+            }
+        }
+        int arg[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int a = 0;
+            float best = fv[0][e];
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (fv[k][e] > best) { best = fv[k][e]; a = k; }
+            arg[e] = a;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!inb[k]) continue;
+            const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
+            const size_t o8 = ((((size_t)n * p.H + yy) * p.W + xx) * p.C) / 8 + c8;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = (window && arg[e] == k) ? g[e] : 0.f;
+            if (p.addend != nullptr) {
+                const float4* ap = reinterpret_cast<const float4*>(p.addend) + o8 * 2;
+                const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+                v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+            }
+            if (p.t_hi != nullptr) {
+                const uint4 fh = __ldg(reinterpret_cast<const uint4*>(p.f_hi) + o8);
+                const uint4 fl = __ldg(reinterpret_cast<const uint4*>(p.f_lo) + o8);
+                const uint4 th = __ldg(reinterpret_cast<const uint4*>(p.t_hi) + o8);
+                const uint4 tl = __ldg(reinterpret_cast<const uint4*>(p.t_lo) + o8);
+                const uint32_t ua[4] = {fh.x, fh.y, fh.z, fh.w}, ub[4] = {fl.x, fl.y, fl.z, fl.w};
+                const uint32_t uc[4] = {th.x, th.y, th.z, th.w}, ud[4] = {tl.x, tl.y, tl.z, tl.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    v[2 * e] += p.content_coef * ((h_lo_f(ua[e]) - h_lo_f(uc[e])) + (h_lo_f(ub[e]) - h_lo_f(ud[e])));
+                    v[2 * e + 1] += p.content_coef * ((h_hi_f(ua[e]) - h_hi_f(uc[e])) + (h_hi_f(ub[e]) - h_hi_f(ud[e])));
+                }
+            }
+            if (p.apply_mask) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (!(fv[k][e] > 0.f)) v[e] = 0.f;
+            }
+            if (p.out_f32 != nullptr) {
+                float4* d = reinterpret_cast<float4*>(p.out_f32) + o8 * 2;
+                d[0] = make_float4(v[0], v[1], v[2], v[3]);
+                d[1] = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_pack<true>(v[2 * e], v[2 * e + 1], h[e], l[e]);
+                reinterpret_cast<uint4*>(p.out_hi)[o8] = make_uint4(h[0], h[1], h[2], h[3]);
+                reinterpret_cast<uint4*>(p.out_lo)[o8] = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Content loss partial sums: sum (F - T)^2 in plane units; one block = one fixed slice; fixed-order tree.
+// Reference: nn.MSELoss() on relu4_2 (main.py:36-37, utils.py:32).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+content_partial_kernel(const uint16_t* __restrict__ f_hi, const uint16_t* __restrict__ f_lo,
+                       const uint16_t* __restrict__ t_hi, const uint16_t* __restrict__ t_lo, size_t n8_per_frame,
+                       float* __restrict__ partial /*[NB][gridDim.x]*/) {
+    __shared__ float sh[8];
+    const int fr = blockIdx.y;
+    const uint4* a = reinterpret_cast<const uint4*>(f_hi) + (size_t)fr * n8_per_frame;
+    const uint4* b = reinterpret_cast<const uint4*>(f_lo) + (size_t)fr * n8_per_frame;
+    const uint4* c = reinterpret_cast<const uint4*>(t_hi) + (size_t)fr * n8_per_frame;
+    const uint4* d = reinterpret_cast<const uint4*>(t_lo) + (size_t)fr * n8_per_frame;
+    float s = 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8_per_frame; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 va = __ldg(a + i), vb = __ldg(b + i), vc = __ldg(c + i), vd = __ldg(d + i);
+        const uint32_t ua[4] = {va.x, va.y, va.z, va.w}, ub[4] = {vb.x, vb.y, vb.z, vb.w};
+        const uint32_t uc[4] = {vc.x, vc.y, vc.z, vc.w}, ud[4] = {vd.x, vd.y, vd.z, vd.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float d0 = (h_lo_f(ua[e]) - h_lo_f(uc[e])) + (h_lo_f(ub[e]) - h_lo_f(ud[e]));
+            const float d1 = (h_hi_f(ua[e]) - h_hi_f(uc[e])) + (h_hi_f(ub[e]) - h_hi_f(ud[e]));
+            s = fmaf(d0, d0, s);
+            s = fmaf(d1, d1, s);
+        }
+    }
+    s = block_reduce_256<false>(s, sh);
+    if (threadIdx.x == 0) partial[(size_t)fr * gridDim.x + blockIdx.x] = s;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Gram finalisation for up to 8 style layers in one launch (blockIdx.y = layer, blockIdx.z = frame).
+//   G = (sum_splits partial) * g_scale               (GramMatrix.forward: bmm then div_(h*w), gram_matrix.py:9-10)
+//   target mode: g_out <- G.   loss mode: diff <- G - A; per-block sum(diff^2) and max|diff|.
+// ------------------------------------------------------------------------------------------------------------
+struct GramLayer {
+    const float* partial;   // [NB][splits][C][C], only tiles with col_tile >= row_tile written
+    const float* target;    // [C][C] shared by all frames (loss mode)
+    float* g_out;           // [NB][C][C] (target mode) or nullptr
+    float* diff;            // [NB][C][C]
+    uint16_t* d_hi;         // [NB][C][C] fp16 planes of (diff + diff^T) * 2^e
+    uint16_t* d_lo;
+    float* blk_sum;         // [NB][GRAM_FIN_BLOCKS]
+    float* blk_max;
+    float* alpha_out;       // [NB] multiplier the Gram-backward GEMM applies to its accumulator
+    float* loss_out;        // &losses[frame * loss_stride + slot], weighted
+    int C, splits;
+    float g_scale;          // 1 / (H*W * s_act^2)
+    float weight;           // loss weight (STYLE_WEIGHTS[k], defaults.py:68)
+    float bwd_coef;         // 2*w / (C^2 * H*W * s_act)
+};
+constexpr int GRAM_FIN_BLOCKS = 32;
+struct GramFinalizeParams {
+    GramLayer L[8];
+    int n_layers, NB, loss_stride;
+};
+
+__global__ void __launch_bounds__(256)
+gram_reduce_kernel(const GramFinalizeParams p) {
+    __shared__ float sh[8];
+    const GramLayer& L = p.L[blockIdx.y];
+    const int fr = blockIdx.z, C = L.C;
+    const size_t CC = (size_t)C * C;
+    float s = 0.f, mx = 0.f;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < CC; e += (size_t)gridDim.x * blockDim.x) {
+        const int c1 = (int)(e / C), c2 = (int)(e % C);
+        const size_t src = ((c1 >> 7) <= (c2 >> 7)) ? e : ((size_t)c2 * C + c1);
+        float g = 0.f;
+        for (int sp = 0; sp < L.splits; ++sp) g += L.partial[((size_t)fr * L.splits + sp) * CC + src];
+        g *= L.g_scale;
+        if (L.g_out != nullptr) {
+            L.g_out[(size_t)fr * CC + e] = g;
+        } else {
+            const float d = g - __ldg(L.target + e);
+            L.diff[(size_t)fr * CC + e] = d;
+            s = fmaf(d, d, s);
+            mx = fmaxf(mx, fabsf(d));
+        }
+    }
+    if (L.g_out == nullptr) {
+        s = block_reduce_256<false>(s, sh);
+        mx = block_reduce_256<true>(mx, sh);
+        if (threadIdx.x == 0) {
+            L.blk_sum[(size_t)fr * GRAM_FIN_BLOCKS + blockIdx.x] = s;
+            L.blk_max[(size_t)fr * GRAM_FIN_BLOCKS + blockIdx.x] = mx;
+        }
+    }
+}
+
+// D = (diff + diff^T) * 2^e as fp16 planes (B operand of the Gram-backward GEMM: dF = coef * D * F,
+// autograd of bmm + div_ + MSELoss), e chosen so |D| < 2^15; alpha_out = coef / 2^e.
+__global__ void __launch_bounds__(256)
+gram_dmat_kernel(const GramFinalizeParams p) {
+    const GramLayer& L = p.L[blockIdx.y];
+    const int fr = blockIdx.z, C = L.C;
+    const size_t CC = (size_t)C * C;
+    float mx = 0.f;
+    for (int b = 0; b < GRAM_FIN_BLOCKS; ++b) mx = fmaxf(mx, L.blk_max[(size_t)fr * GRAM_FIN_BLOCKS + b]);
+    int e2 = 0;
+    if (mx > 0.f && isfinite(mx)) e2 = 13 - ilogbf(mx);
+    const float sc = ldexpf(1.f, e2);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double s = 0.0;
+        for (int b = 0; b < GRAM_FIN_BLOCKS; ++b) s += (double)L.blk_sum[(size_t)fr * GRAM_FIN_BLOCKS + b];
+        const float mean = (float)(s / (double)CC);
+        *(L.loss_out + (size_t)fr * p.loss_stride) = L.weight * mean;
+        L.alpha_out[fr] = L.bwd_coef * ldexpf(1.f, -e2);
+    }
+    const float* df = L.diff + (size_t)fr * CC;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < CC; e += (size_t)gridDim.x * blockDim.x) {
+        const int c1 = (int)(e / C), c2 = (int)(e % C);
+        const float v = (df[e] + df[(size_t)c2 * C + c1]) * sc;
+        const __half h = __float2half_rn(v);
+        const __half l = __float2half_rn(v - __half2float(h));
+        L.d_hi[(size_t)fr * CC + e] = __half_as_ushort(h);
+        L.d_lo[(size_t)fr * CC + e] = __half_as_ushort(l);
+    }
+}
+
+// total = sum_k losses[k] in list order (python sum(layer_losses), utils.py:32-35); content losses come from partials.
+struct LossTotalParams {
+    float* losses;           // [NB][loss_stride]
+    int loss_stride, n_losses, NB;
+    const float* c_partial[4];   // per content slot: [NB][c_blocks]
+    int c_slot[4];
+    float c_scale[4];        // weight / (C*H*W * s_act^2)
+    int n_content, c_blocks;
+};
+__global__ void loss_total_kernel(const LossTotalParams p) {
+    const int fr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fr >= p.NB) return;
+    float* L = p.losses + (size_t)fr * p.loss_stride;
+    for (int k = 0; k < p.n_content; ++k) {
+        double s = 0.0;
+        for (int b = 0; b < p.c_blocks; ++b) s += (double)p.c_partial[k][(size_t)fr * p.c_blocks + b];
+        L[p.c_slot[k]] = (float)(s * (double)p.c_scale[k]);
+    }
+    float t = 0.f;
+    for (int k = 0; k < p.n_losses; ++k) t += L[k];
+    L[p.n_losses] = t;
+}
+
+}  // namespace ist

@@ -1,0 +1,178 @@
+// Gram matrix partial products G_part[split] = F^T F over a pixel range, as a tcgen05 SYRK.
+//
+// Replaces torch.bmm(F, F.transpose(1, 2)) of the reference (IST/model/meta_arch/gram_matrix.py:9).
+// F lives in HBM as NHWC 16-bit planes (hi, lo): element (pixel n, channel c) at n*C + c. The contraction
+// index is the pixel, so both operands are *MN-major* for the tensor core (channel contiguous): a TMA box
+// of [64 pixels][64 channels] with 128-byte swizzle is exactly one column of MN-major SW128 atoms
+// (8 pixel rows of 128 B each), SBO = 1024 between 8-pixel groups, LBO = 8192 between 64-channel groups.
+// Only tiles with n_tile >= m_tile are computed (SYRK); gram_finalize mirrors them. Diagonal tiles reuse
+// the A tile as B (no second load). Split over pixels gives >= 1 CTA per SM even for C = 64; partial
+// results go to a [split] array that gram_finalize sums in a fixed order (deterministic, no atomics).
+// 3-pass split (hi*hi + hi*lo + lo*hi) as in conv_igemm.cuh.
+#pragma once
+#include "ptx.cuh"
+
+namespace ist {
+
+struct GramParams {
+    int NB, HW, C;
+    int tiles_c;           // ceil(C / 128)
+    int n_tile;            // min(C, 128)
+    int splits;            // pixel splits per frame
+    int chunks_per_split;  // 64-pixel chunks per split
+    int passes;
+    uint32_t idesc;        // M = 128, N = n_tile, both MN-major
+    float* partial;        // [NB][splits][C][C]
+};
+
+struct GramCfg {
+    static constexpr int T_BYTES = 128 * 128;            // [64 pixels][128 channels] x 2 B, as two 8 KB channel groups
+    static constexpr int STAGE_BYTES = 4 * T_BYTES;      // A_hi, A_lo, B_hi, B_lo
+    static constexpr int STAGES = 3;
+    static constexpr int TMEM_COLS = 128;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(192, 1)
+gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                 const GramParams p) {
+    using Cfg = GramCfg;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+    const uint32_t tfull_bar = bar_base + 128u;
+    const uint32_t tmem_slot = bar_base + 160u;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
+        smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * Cfg::STAGE_BYTES + 160);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // tile decode: blockIdx.x = split, blockIdx.y = triangular tile id, blockIdx.z = frame
+    int mt = 0, nt = 0;
+    {
+        int t = blockIdx.y;
+        for (int i = 0; i < p.tiles_c; ++i) {
+            const int row = p.tiles_c - i;
+            if (t < row) { mt = i; nt = i + t; break; }
+            t -= row;
+        }
+    }
+    const bool diag = (mt == nt);
+    const int split = blockIdx.x, fr = blockIdx.z;
+    const int total_chunks = (p.HW + 63) >> 6;
+    const int c_begin = split * p.chunks_per_split;
+    int c_end = c_begin + p.chunks_per_split;
+    if (c_end > total_chunks) c_end = total_chunks;
+    const int kiters = c_end > c_begin ? c_end - c_begin : 0;
+    const int groups_a = (p.C >= 128) ? 2 : 1;           // 64-channel groups actually loaded per operand
+    const int groups_b = p.n_tile >> 6;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_hi);
+        if (p.passes == 3) tma_prefetch_desc(&tm_lo);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tfull_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc<Cfg::TMEM_COLS>(tmem_slot); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int planes = (p.passes == 3) ? 2 : 1;
+            const uint32_t tx = (uint32_t)(planes * (groups_a + (diag ? 0 : groups_b)) * 8192);
+            for (int kit = 0; kit < kiters; ++kit) {
+                const int pix = (c_begin + kit) * 64;
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t s0 = smem_base + stage * Cfg::STAGE_BYTES;
+                mbar_arrive_expect_tx(full_bar(stage), tx);
+                for (int pl = 0; pl < planes; ++pl) {
+                    const CUtensorMap* tm = pl == 0 ? &tm_hi : &tm_lo;
+                    for (int g = 0; g < groups_a; ++g)
+                        tma_load_3d(s0 + pl * Cfg::T_BYTES + g * 8192, tm, full_bar(stage), mt * 128 + g * 64, pix, fr);
+                    if (!diag)
+                        for (int g = 0; g < groups_b; ++g)
+                            tma_load_3d(s0 + (2 + pl) * Cfg::T_BYTES + g * 8192, tm, full_bar(stage),
+                                        nt * 128 + g * 64, pix, fr);
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kit = 0; kit < kiters; ++kit) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
+                const uint32_t sB = diag ? sA : sA + 2 * Cfg::T_BYTES;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {          // 16 pixels per MMA = two 8-row groups = 2048 B
+                    const uint64_t a_hi = umma_smem_desc_sw128(sA + k4 * 2048, 8192, 1024);
+                    const uint64_t b_hi = umma_smem_desc_sw128(sB + k4 * 2048, 8192, 1024);
+                    umma_f16(tmem_base, a_hi, b_hi, p.idesc, (kit | k4) != 0 ? 1u : 0u);
+                    if (p.passes == 3) {
+                        const uint64_t a_lo = umma_smem_desc_sw128(sA + Cfg::T_BYTES + k4 * 2048, 8192, 1024);
+                        const uint64_t b_lo = umma_smem_desc_sw128(sB + Cfg::T_BYTES + k4 * 2048, 8192, 1024);
+                        umma_f16(tmem_base, a_hi, b_lo, p.idesc, 1u);
+                        umma_f16(tmem_base, a_lo, b_hi, p.idesc, 1u);
+                    }
+                }
+                umma_commit(empty_bar(stage));
+                if (kit == kiters - 1) { umma_commit(tfull_bar); }
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int c1 = mt * 128 + quad * 32 + lane;
+        const bool valid = (quad * 32 + lane) < (p.C >= 128 ? 128 : 64) && c1 < p.C;
+        float* dst = p.partial + (((size_t)fr * p.splits + split) * p.C + (valid ? c1 : 0)) * (size_t)p.C + nt * 128;
+        if (kiters > 0) {
+            mbar_wait(tfull_bar, 0);
+            tc_fence_after();
+        }
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+            uint32_t r[32];
+            if (kiters > 0) {
+                tmem_ld_32x32(t_row + c0, r);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+            if (valid) {
+                float4* d = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    d[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                       __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+}  // namespace ist

@@ -1,0 +1,212 @@
+// Host-side helpers shared by the plan, the L-BFGS driver and the per-op entry points:
+// error reporting across the C ABI, TMA tensor-map construction, kernel launchers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ist_b200.h"
+#include "conv_igemm.cuh"
+#include "elementwise.cuh"
+#include "gram.cuh"
+
+namespace ist {
+
+inline std::string& last_error() {
+    static thread_local std::string e;
+    return e;
+}
+inline int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error() = buf;
+    return code;
+}
+#define IST_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return ::ist::fail(IST_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define IST_TRY(call)                  \
+    do {                               \
+        int rc__ = (call);             \
+        if (rc__ != IST_OK) return rc__; \
+    } while (0)
+
+inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no -lcuda needed)
+// ----------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// 16-bit elements, 128-byte swizzle, zero fill out of bounds. dims/box innermost first; strides in bytes for dims 1..rank-1.
+inline int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box) {
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) return fail(IST_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                    ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(IST_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r,
+                    rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                    box[0], box[1], rank > 2 ? box[2] : 0);
+    return IST_OK;
+}
+
+inline void pick_tile(int W, int* TW, int* TH) {
+    if (W >= 16) { *TW = 16; *TH = 8; } else { *TW = 8; *TH = 16; }
+}
+// NHWC planes [NB,H,W,C] as (C, W, H, NB), box (64, TW, TH, 1): the A operand of the implicit GEMM
+inline int map_act(CUtensorMap* m, const uint16_t* base, int NB, int H, int W, int C, int TW, int TH) {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+    const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, 1};
+    return make_tmap(m, base, 4, dims, strides, box);
+}
+// weight planes [G][N][K] as (K, N, G), box (64, n_tile, 1): the B operand (G = tap, or frame for the Gram backward)
+inline int map_b(CUtensorMap* m, const uint16_t* base, int G, int N, int K, int n_tile) {
+    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)G};
+    const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)N * K * 2};
+    const uint32_t box[3] = {64, (uint32_t)n_tile, 1};
+    return make_tmap(m, base, 3, dims, strides, box);
+}
+// planes viewed as [NB][HW][C] -> (C, HW, NB), box (64, 64, 1): both operands of the Gram SYRK
+inline int map_gram(CUtensorMap* m, const uint16_t* base, int NB, int HW, int C) {
+    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)HW, (uint64_t)NB};
+    const uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)HW * C * 2};
+    const uint32_t box[3] = {64, 64, 1};
+    return make_tmap(m, base, 3, dims, strides, box);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// launchers
+// ----------------------------------------------------------------------------------------------------------
+template <int N_TILE>
+inline int launch_conv_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                         const CUtensorMap& b_lo, const ConvParams& p) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        IST_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      ConvCfg<N_TILE>::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int total = p.NB * p.tiles_x * p.tiles_y * p.tiles_n;
+    const int grid = total < num_sms() ? total : num_sms();
+    conv_igemm_kernel<N_TILE><<<grid, 192, ConvCfg<N_TILE>::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    IST_CUDA(cudaGetLastError());
+    return IST_OK;
+}
+inline int conv_n_tile(int cout) { return cout >= 128 ? 128 : 64; }
+// Fills the tiling fields of p (NB,H,W,Cin,Cout,taps,passes,mode and epilogue pointers must be set) and launches.
+inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                       const CUtensorMap& b_lo, ConvParams p, bool bf16) {
+    if (p.Cin % 64 != 0 || p.Cout % 64 != 0) return fail(IST_ERR_ARG, "conv_igemm needs Cin, Cout %% 64 == 0 (got %d, %d)", p.Cin, p.Cout);
+    pick_tile(p.W, &p.TW, &p.TH);
+    p.tiles_x = (p.W + p.TW - 1) / p.TW;
+    p.tiles_y = (p.H + p.TH - 1) / p.TH;
+    const int nt = conv_n_tile(p.Cout);
+    p.tiles_n = p.Cout / nt;
+    p.idesc = umma_idesc_f16(bf16 ? UMMA_FMT_BF16 : UMMA_FMT_F16, 128, nt, 0, 0);
+    return nt == 128 ? launch_conv_t<128>(st, a_hi, a_lo, b_hi, b_lo, p) : launch_conv_t<64>(st, a_hi, a_lo, b_hi, b_lo, p);
+}
+
+inline void gram_split_plan(int NB, int HW, int C, int* splits, int* chunks_per_split) {
+    const int tiles_c = (C + 127) / 128;
+    const int tri = tiles_c * (tiles_c + 1) / 2;
+    const int total_chunks = (HW + 63) / 64;
+    int want = (2 * num_sms() + tri * NB - 1) / (tri * NB);
+    if (want < 1) want = 1;
+    if (want > total_chunks) want = total_chunks;
+    if (want > 64) want = 64;
+    const int cps = (total_chunks + want - 1) / want;
+    *chunks_per_split = cps;
+    *splits = (total_chunks + cps - 1) / cps;
+}
+inline int launch_gram(cudaStream_t st, const CUtensorMap& m_hi, const CUtensorMap& m_lo, int NB, int HW, int C,
+                       int splits, int chunks_per_split, float* partial, int passes) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        IST_CUDA(cudaFuncSetAttribute(gram_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    if (C % 64 != 0 || (C > 64 && C % 128 != 0)) return fail(IST_ERR_ARG, "gram needs C == 64 or C %% 128 == 0 (got %d)", C);
+    GramParams p;
+    p.NB = NB; p.HW = HW; p.C = C;
+    p.tiles_c = (C + 127) / 128;
+    p.n_tile = C < 128 ? 64 : 128;
+    p.splits = splits;
+    p.chunks_per_split = chunks_per_split;
+    p.passes = passes;
+    p.idesc = umma_idesc_f16(UMMA_FMT_F16, 128, p.n_tile, 1, 1);
+    p.partial = partial;
+    const int tri = p.tiles_c * (p.tiles_c + 1) / 2;
+    dim3 grid(splits, tri, NB);
+    gram_syrk_kernel<<<grid, 192, GramCfg::SMEM_BYTES, st>>>(m_hi, m_lo, p);
+    IST_CUDA(cudaGetLastError());
+    return IST_OK;
+}
+
+inline int ew_grid(size_t work_items, int block) {
+    size_t g = (work_items + block - 1) / block;
+    const size_t cap = (size_t)num_sms() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+struct DevMem {
+    std::vector<void*> ptrs;
+    size_t bytes = 0;
+    ~DevMem() { release(); }
+    void release() {
+        for (void* p : ptrs) cudaFree(p);
+        ptrs.clear();
+        bytes = 0;
+    }
+    template <typename T>
+    int alloc(T** out, size_t count) {
+        void* p = nullptr;
+        const size_t b = ((count * sizeof(T) + 255) / 256) * 256 + 256;
+        cudaError_t e = cudaMalloc(&p, b);
+        if (e != cudaSuccess) return fail(IST_ERR_CUDA, "cudaMalloc(%zu) failed: %s", b, cudaGetErrorString(e));
+        ptrs.push_back(p);
+        bytes += b;
+        *out = reinterpret_cast<T*>(p);
+        return IST_OK;
+    }
+};
+
+}  // namespace ist

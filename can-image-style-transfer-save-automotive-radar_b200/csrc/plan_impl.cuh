@@ -1,0 +1,608 @@
+// Plan = VGG feature stack + loss configuration + cached targets for one (batch, H, W), all buffers resident in HBM.
+// Implements the C ABI of include/ist_b200.h for: VGG.forward (IST/model/meta_arch/vgg.py:44-58), GramMatrix /
+// GramMSELoss / MSELoss (gram_matrix.py:6-11, gram_mse_loss.py:6-8, main.py:36-37) and the closure of
+// IST/model/engine/utils.py:29-41 (loss + d loss / d image).
+#include "host_common.cuh"
+
+using namespace ist;
+
+namespace {
+
+constexpr float kActScale = 0.25f;   // static power-of-two scale of fp16 activation planes (range to 2.6e5, floor 2.4e-7)
+constexpr int kMaxLoss = 15;
+constexpr int kContentBlocks = 64;
+
+struct Planes {
+    uint16_t* hi = nullptr;
+    uint16_t* lo = nullptr;
+};
+
+struct Layer {
+    int kind = 0, cin = 0, cout = 0;
+    int H = 0, W = 0;          // output spatial size
+    int Hin = 0, Win = 0;      // input spatial size
+    int C = 0;                 // output channels
+    int conv_index = -1;
+    Planes out;                // fp16 planes of the layer output (after ReLU / after pool)
+    size_t out_elems = 0;      // NB*H*W*C
+    // conv parameters
+    float* w_f32 = nullptr;    // OIHW copy (first conv only)
+    float* bias = nullptr;
+    uint16_t *wf_hi = nullptr, *wf_lo = nullptr, *wd_hi = nullptr, *wd_lo = nullptr;
+    float w_scale = 1.f;
+    bool has_weights = false;
+    CUtensorMap mA_hi, mA_lo;      // forward A: planes of the layer input
+    CUtensorMap mBf_hi, mBf_lo;    // forward B
+    CUtensorMap mBd_hi, mBd_lo;    // dgrad B
+    CUtensorMap mG_hi, mG_lo;      // dgrad A: dY planes of this conv
+    Planes dY;                     // bf16 planes, gradient w.r.t. this conv's pre-activation
+    // feature-as-operand maps (Gram forward / Gram backward)
+    CUtensorMap mGram_hi, mGram_lo, mFeat_hi, mFeat_lo, mD_hi, mD_lo;
+    // losses
+    int style_slot = -1, content_slot = -1;
+    float style_w = 0.f, content_w = 0.f;
+    int splits = 0, chunks_per_split = 0;
+    float *gram_partial = nullptr, *gram_diff = nullptr, *blk_sum = nullptr, *blk_max = nullptr, *alpha = nullptr;
+    float* target = nullptr;
+    bool target_set = false;
+    uint16_t *d_hi = nullptr, *d_lo = nullptr;
+    Planes T;
+    bool content_set = false;
+    float* c_partial = nullptr;
+    float* ext_seed = nullptr;     // fp32 NHWC external gradient seed (generic backward)
+    bool ext_active = false;
+};
+
+}  // namespace
+
+struct ist_plan {
+    int NB = 0, H = 0, W = 0;
+    std::vector<Layer> layers;
+    int n_conv = 0;
+    DevMem mem;
+    Planes gbuf[2];
+    float* fbuf[2] = {nullptr, nullptr};
+    size_t max_elems = 0;
+    int n_style = 0, n_content = 0;
+    std::vector<int> style_layers, content_layers;
+    float* losses = nullptr;       // [NB][kMaxLoss+1] device scratch
+    int forwarded_upto = -1;
+    int passes_fwd = 3, passes_bwd = 3;
+};
+
+namespace {
+
+int check_device() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(IST_ERR_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) return fail(IST_ERR_DEVICE, "sm_100a kernels need a compute-capability 10.x device (found %d.x); there is no fallback", major);
+    return IST_OK;
+}
+
+int alloc_planes(DevMem& mem, Planes* p, size_t elems) {
+    IST_TRY(mem.alloc(&p->hi, elems));
+    IST_TRY(mem.alloc(&p->lo, elems));
+    return IST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+int run_forward(ist_plan* P, const float* x, int upto, cudaStream_t st) {
+    for (int l = 0; l <= upto; ++l) {
+        Layer& L = P->layers[l];
+        if (L.kind == IST_LAYER_CONV3X3_RELU) {
+            if (!L.has_weights) return fail(IST_ERR_STATE, "conv layer %d has no weights (ist_plan_set_weights)", l);
+            if (l == 0) {
+                const size_t px = (size_t)P->NB * L.H * L.W;
+                conv_first_fwd_kernel<64><<<(unsigned)((px + 127) / 128), 128, 0, st>>>(x, L.w_f32, L.bias, L.out.hi, L.out.lo,
+                                                                                     P->NB, L.H, L.W, kActScale);
+                IST_CUDA(cudaGetLastError());
+            } else {
+                ConvParams p;
+                memset(&p, 0, sizeof(p));
+                p.NB = P->NB; p.H = L.H; p.W = L.W; p.Cin = L.cin; p.Cout = L.cout; p.taps = 9;
+                p.passes = P->passes_fwd;
+                p.mode = CONV_FWD;
+                p.alpha = 1.f / (kActScale * L.w_scale);
+                p.bias = L.bias;
+                p.out_scale = kActScale;
+                p.out_hi = L.out.hi; p.out_lo = L.out.lo;
+                IST_TRY(launch_conv(st, L.mA_hi, L.mA_lo, L.mBf_hi, L.mBf_lo, p, false));
+            }
+        } else {
+            const Layer& I = P->layers[l - 1];
+            const size_t items = (size_t)P->NB * L.H * L.W * (L.C / 8);
+            maxpool_fwd_kernel<<<ew_grid(items, 256), 256, 0, st>>>(I.out.hi, I.out.lo, L.out.hi, L.out.lo, P->NB, I.H, I.W, I.C);
+            IST_CUDA(cudaGetLastError());
+        }
+    }
+    P->forwarded_upto = upto;
+    return IST_OK;
+}
+
+// Gram partials of one layer's current features
+int run_gram_partial(ist_plan* P, Layer& L, cudaStream_t st) {
+    return launch_gram(st, L.mGram_hi, L.mGram_lo, P->NB, L.H * L.W, L.C, L.splits, L.chunks_per_split, L.gram_partial,
+                       P->passes_fwd);
+}
+
+void fill_gram_layer(const ist_plan* P, const Layer& L, GramLayer* g, float* g_out, float* loss_base) {
+    memset(g, 0, sizeof(*g));
+    g->partial = L.gram_partial;
+    g->target = L.target;
+    g->g_out = g_out;
+    g->diff = L.gram_diff;
+    g->d_hi = L.d_hi; g->d_lo = L.d_lo;
+    g->blk_sum = L.blk_sum; g->blk_max = L.blk_max;
+    g->alpha_out = L.alpha;
+    g->loss_out = loss_base != nullptr ? loss_base + L.style_slot : nullptr;
+    g->C = L.C; g->splits = L.splits;
+    const double hw = (double)L.H * L.W;
+    g->g_scale = (float)(1.0 / (hw * kActScale * kActScale));
+    g->weight = L.style_w;
+    g->bwd_coef = (float)(2.0 * L.style_w / ((double)L.C * L.C * hw * kActScale));
+    (void)P;
+}
+
+int ensure_gram_buffers(ist_plan* P, Layer& L) {
+    if (L.gram_partial != nullptr) return IST_OK;
+    if (L.kind != IST_LAYER_CONV3X3_RELU && L.kind != IST_LAYER_MAXPOOL2X2) return fail(IST_ERR_ARG, "bad layer");
+    gram_split_plan(P->NB, L.H * L.W, L.C, &L.splits, &L.chunks_per_split);
+    const size_t CC = (size_t)L.C * L.C;
+    IST_TRY(P->mem.alloc(&L.gram_partial, (size_t)P->NB * L.splits * CC));
+    IST_CUDA(cudaMemset(L.gram_partial, 0, (size_t)P->NB * L.splits * CC * sizeof(float)));
+    IST_TRY(P->mem.alloc(&L.gram_diff, (size_t)P->NB * CC));
+    IST_TRY(P->mem.alloc(&L.blk_sum, (size_t)P->NB * GRAM_FIN_BLOCKS));
+    IST_TRY(P->mem.alloc(&L.blk_max, (size_t)P->NB * GRAM_FIN_BLOCKS));
+    IST_TRY(P->mem.alloc(&L.alpha, (size_t)P->NB));
+    IST_TRY(P->mem.alloc(&L.target, CC));
+    IST_TRY(P->mem.alloc(&L.d_hi, (size_t)P->NB * CC));
+    IST_TRY(P->mem.alloc(&L.d_lo, (size_t)P->NB * CC));
+    IST_TRY(map_gram(&L.mGram_hi, L.out.hi, P->NB, L.H * L.W, L.C));
+    IST_TRY(map_gram(&L.mGram_lo, L.out.lo, P->NB, L.H * L.W, L.C));
+    int TW, TH;
+    pick_tile(L.W, &TW, &TH);
+    IST_TRY(map_act(&L.mFeat_hi, L.out.hi, P->NB, L.H, L.W, L.C, TW, TH));
+    IST_TRY(map_act(&L.mFeat_lo, L.out.lo, P->NB, L.H, L.W, L.C, TW, TH));
+    IST_TRY(map_b(&L.mD_hi, L.d_hi, P->NB, L.C, L.C, conv_n_tile(L.C)));
+    IST_TRY(map_b(&L.mD_lo, L.d_lo, P->NB, L.C, L.C, conv_n_tile(L.C)));
+    return IST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward: produces dY planes for every conv from the deepest seeded layer down, then the image gradient
+// ------------------------------------------------------------------------------------------------------------
+struct Seeds {
+    bool use_losses = false;   // style / content seeds from the plan's loss configuration
+};
+
+int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStream_t st) {
+    const int NB = P->NB;
+    auto has_style = [&](const Layer& L) { return S.use_losses && L.style_slot >= 0; };
+    auto has_content = [&](const Layer& L) { return S.use_losses && L.content_slot >= 0; };
+    auto ext = [&](const Layer& L) -> const float* { return L.ext_active ? L.ext_seed : nullptr; };
+
+    auto set_content = [&](const Layer& L, const uint16_t** fh, const uint16_t** fl, const uint16_t** th, const uint16_t** tl,
+                           float* coef) {
+        *fh = L.out.hi; *fl = L.out.lo; *th = L.T.hi; *tl = L.T.lo;
+        *coef = (float)(2.0 * L.content_w / ((double)L.C * L.H * L.W * kActScale));
+    };
+    // dgrad of conv `cj` (layer index) into the gradient of its input tensor
+    auto dgrad = [&](const Layer& Cj, ConvParams p) -> int {
+        p.NB = NB; p.H = Cj.H; p.W = Cj.W; p.Cin = Cj.cout; p.Cout = Cj.cin; p.taps = 9;
+        p.passes = P->passes_bwd; p.mode = CONV_GRAD; p.alpha = 1.f;
+        return launch_conv(st, Cj.mG_hi, Cj.mG_lo, Cj.mBd_hi, Cj.mBd_lo, p, true);
+    };
+    auto gram_bwd = [&](Layer& L, const float* addend, bool content) -> int {
+        ConvParams p;
+        memset(&p, 0, sizeof(p));
+        p.NB = NB; p.H = L.H; p.W = L.W; p.Cin = L.C; p.Cout = L.C; p.taps = 1; p.b_frame = 1;
+        p.passes = P->passes_bwd; p.mode = CONV_GRAD; p.alpha = 1.f;
+        p.alpha_dev = L.alpha; p.alpha_stride = 1;
+        p.addend = addend;
+        if (content) set_content(L, &p.f_hi, &p.f_lo, &p.t_hi, &p.t_lo, &p.content_coef);
+        p.mask_hi = L.out.hi;
+        p.out_hi = L.dY.hi; p.out_lo = L.dY.lo;
+        return launch_conv(st, L.mFeat_hi, L.mFeat_lo, L.mD_hi, L.mD_lo, p, false);
+    };
+    auto route = [&](Layer& L, const float* g_pool, const float* addend, bool content, bool to_f32, float* f32_out) -> int {
+        RouteParams r;
+        memset(&r, 0, sizeof(r));
+        r.NB = NB; r.H = L.H; r.W = L.W; r.C = L.C;
+        r.g_pool = g_pool;
+        r.f_hi = L.out.hi; r.f_lo = L.out.lo;
+        r.addend = addend;
+        if (content) {
+            const uint16_t *fh, *fl;
+            set_content(L, &fh, &fl, &r.t_hi, &r.t_lo, &r.content_coef);
+        }
+        r.apply_mask = to_f32 ? 0 : 1;
+        r.out_hi = L.dY.hi; r.out_lo = L.dY.lo;
+        r.out_f32 = to_f32 ? f32_out : nullptr;
+        const size_t items = (size_t)NB * ((L.H + 1) / 2) * ((L.W + 1) / 2) * (L.C / 8);
+        grad_route_kernel<<<ew_grid(items, 256), 256, 0, st>>>(r);
+        IST_CUDA(cudaGetLastError());
+        return IST_OK;
+    };
+
+    for (int l = deepest; l >= 0; --l) {
+        Layer& L = P->layers[l];
+        if (L.kind != IST_LAYER_CONV3X3_RELU) continue;
+        const bool style = has_style(L), content = has_content(L);
+        if (content && !L.content_set) return fail(IST_ERR_STATE, "content target of layer %d not captured", l);
+        if (style && !L.target_set) return fail(IST_ERR_STATE, "style target of layer %d not set", l);
+        const bool has_up = l < deepest;
+        if (has_up && P->layers[l + 1].kind == IST_LAYER_CONV3X3_RELU) {
+            const Layer& Cn = P->layers[l + 1];
+            ConvParams p;
+            memset(&p, 0, sizeof(p));
+            p.addend = ext(L);
+            if (content) set_content(L, &p.f_hi, &p.f_lo, &p.t_hi, &p.t_lo, &p.content_coef);
+            if (style) {
+                p.out_f32 = P->fbuf[1];
+                IST_TRY(dgrad(Cn, p));
+                IST_TRY(gram_bwd(L, P->fbuf[1], false));
+            } else {
+                p.mask_hi = L.out.hi;
+                p.out_hi = L.dY.hi; p.out_lo = L.dY.lo;
+                IST_TRY(dgrad(Cn, p));
+            }
+        } else if (has_up) {
+            // consumer is a pool; the pool's consumer (if any) is conv l+2
+            Layer& Pl = P->layers[l + 1];
+            const float* g_pool = nullptr;
+            if (l + 2 <= deepest) {
+                const Layer& Cn = P->layers[l + 2];
+                if (Cn.kind != IST_LAYER_CONV3X3_RELU) return fail(IST_ERR_ARG, "pool followed by pool is not supported");
+                ConvParams p;
+                memset(&p, 0, sizeof(p));
+                p.addend = ext(Pl);
+                p.out_f32 = P->fbuf[0];
+                IST_TRY(dgrad(Cn, p));
+                g_pool = P->fbuf[0];
+            } else {
+                g_pool = ext(Pl);
+            }
+            if (style) {
+                IST_TRY(route(L, g_pool, ext(L), content, true, P->fbuf[1]));
+                IST_TRY(gram_bwd(L, P->fbuf[1], false));
+            } else {
+                IST_TRY(route(L, g_pool, ext(L), content, false, nullptr));
+            }
+        } else {
+            if (style) {
+                IST_TRY(gram_bwd(L, ext(L), content));
+            } else {
+                IST_TRY(route(L, nullptr, ext(L), content, false, nullptr));
+            }
+        }
+    }
+    Layer& L0 = P->layers[0];
+    const size_t px = (size_t)NB * L0.H * L0.W;
+    conv_first_dgrad_kernel<64><<<(unsigned)((px + 127) / 128), 128, 0, st>>>(L0.dY.hi, L0.dY.lo, L0.w_f32, grad, NB, L0.H, L0.W);
+    IST_CUDA(cudaGetLastError());
+    return IST_OK;
+}
+
+int run_losses(ist_plan* P, float* losses_dev, cudaStream_t st) {
+    const int stride = P->n_style + P->n_content + 1;
+    GramFinalizeParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.NB = P->NB;
+    gp.loss_stride = stride;
+    for (int k = 0; k < P->n_style; ++k) {
+        Layer& L = P->layers[P->style_layers[k]];
+        if (!L.target_set) return fail(IST_ERR_STATE, "style target %d not set", k);
+        IST_TRY(run_gram_partial(P, L, st));
+        fill_gram_layer(P, L, &gp.L[gp.n_layers++], nullptr, losses_dev);
+    }
+    if (gp.n_layers > 0) {
+        dim3 grid(GRAM_FIN_BLOCKS, gp.n_layers, P->NB);
+        gram_reduce_kernel<<<grid, 256, 0, st>>>(gp);
+        IST_CUDA(cudaGetLastError());
+        gram_dmat_kernel<<<grid, 256, 0, st>>>(gp);
+        IST_CUDA(cudaGetLastError());
+    }
+    LossTotalParams lt;
+    memset(&lt, 0, sizeof(lt));
+    lt.losses = losses_dev;
+    lt.loss_stride = stride;
+    lt.n_losses = P->n_style + P->n_content;
+    lt.NB = P->NB;
+    lt.c_blocks = kContentBlocks;
+    for (int k = 0; k < P->n_content; ++k) {
+        Layer& L = P->layers[P->content_layers[k]];
+        if (!L.content_set) return fail(IST_ERR_STATE, "content target %d not captured", k);
+        const size_t n8 = (size_t)L.H * L.W * L.C / 8;
+        dim3 grid(kContentBlocks, P->NB);
+        content_partial_kernel<<<grid, 256, 0, st>>>(L.out.hi, L.out.lo, L.T.hi, L.T.lo, n8, L.c_partial);
+        IST_CUDA(cudaGetLastError());
+        lt.c_partial[k] = L.c_partial;
+        lt.c_slot[k] = P->n_style + k;
+        lt.c_scale[k] = (float)((double)L.content_w / ((double)L.C * L.H * L.W * kActScale * kActScale));
+        lt.n_content++;
+    }
+    loss_total_kernel<<<(P->NB + 63) / 64, 64, 0, st>>>(lt);
+    IST_CUDA(cudaGetLastError());
+    return IST_OK;
+}
+
+int deepest_loss_layer(const ist_plan* P) {
+    int d = -1;
+    for (int l : P->style_layers) d = l > d ? l : d;
+    for (int l : P->content_layers) d = l > d ? l : d;
+    return d;
+}
+
+}  // namespace
+
+// ================================================================================================================
+// C ABI
+// ================================================================================================================
+extern "C" {
+
+const char* ist_last_error(void) { return last_error().c_str(); }
+int ist_version(void) { return 1; }
+int ist_device_check(void) { return check_device(); }
+
+int ist_plan_create(ist_plan** out, int n_layers, const ist_layer_desc* layers, int batch, int H, int W) {
+    if (out == nullptr || layers == nullptr || n_layers < 1 || batch < 1 || H < 1 || W < 1)
+        return fail(IST_ERR_ARG, "ist_plan_create: bad arguments");
+    IST_TRY(check_device());
+    if (layers[0].kind != IST_LAYER_CONV3X3_RELU || layers[0].cin != 3 || layers[0].cout != 64)
+        return fail(IST_ERR_ARG, "first layer must be conv 3->64 (got kind %d %d->%d)", layers[0].kind, layers[0].cin, layers[0].cout);
+    ist_plan* P = new ist_plan();
+    P->NB = batch; P->H = H; P->W = W;
+    const char* pf = getenv("IST_B200_PASSES_FWD");
+    const char* pb = getenv("IST_B200_PASSES_BWD");
+    if (pf != nullptr && atoi(pf) == 1) P->passes_fwd = 1;
+    if (pb != nullptr && atoi(pb) == 1) P->passes_bwd = 1;
+    int h = H, w = W, c = 3, nconv = 0;
+    int rc = IST_OK;
+    P->layers.resize(n_layers);
+    for (int l = 0; l < n_layers && rc == IST_OK; ++l) {
+        Layer& L = P->layers[l];
+        L.kind = layers[l].kind;
+        L.Hin = h; L.Win = w;
+        if (L.kind == IST_LAYER_CONV3X3_RELU) {
+            L.cin = layers[l].cin; L.cout = layers[l].cout;
+            if (L.cin != c) rc = fail(IST_ERR_ARG, "layer %d: cin %d does not match previous channels %d", l, L.cin, c);
+            if (l > 0 && (L.cin % 64 != 0 || L.cout % 64 != 0)) rc = fail(IST_ERR_ARG, "layer %d: channels must be multiples of 64", l);
+            L.conv_index = nconv++;
+            c = L.cout;
+        } else if (L.kind == IST_LAYER_MAXPOOL2X2) {
+            if (l == 0 || P->layers[l - 1].kind != IST_LAYER_CONV3X3_RELU) rc = fail(IST_ERR_ARG, "layer %d: pool must follow a conv", l);
+            h /= 2; w /= 2;
+            if (h < 1 || w < 1) rc = fail(IST_ERR_ARG, "layer %d: image too small for this many pools", l);
+        } else {
+            rc = fail(IST_ERR_ARG, "layer %d: unknown kind %d", l, L.kind);
+        }
+        L.H = h; L.W = w; L.C = c;
+        L.out_elems = (size_t)batch * h * w * c;
+        if (L.out_elems > P->max_elems) P->max_elems = L.out_elems;
+    }
+    P->n_conv = nconv;
+    // buffers
+    for (int l = 0; l < n_layers && rc == IST_OK; ++l) rc = alloc_planes(P->mem, &P->layers[l].out, P->layers[l].out_elems);
+    for (int i = 0; i < 2 && rc == IST_OK; ++i) {
+        rc = alloc_planes(P->mem, &P->gbuf[i], P->max_elems);
+        if (rc == IST_OK) rc = P->mem.alloc(&P->fbuf[i], P->max_elems);
+    }
+    if (rc == IST_OK) rc = P->mem.alloc(&P->losses, (size_t)batch * (kMaxLoss + 1));
+    for (int l = 0; l < n_layers && rc == IST_OK; ++l) {
+        Layer& L = P->layers[l];
+        if (L.kind != IST_LAYER_CONV3X3_RELU) continue;
+        L.dY = P->gbuf[L.conv_index & 1];
+        rc = P->mem.alloc(&L.bias, (size_t)L.cout);
+        if (rc != IST_OK) break;
+        if (l == 0) {
+            rc = P->mem.alloc(&L.w_f32, (size_t)L.cout * L.cin * 9);
+            continue;
+        }
+        const size_t wn = (size_t)L.cout * L.cin * 9;
+        if (rc == IST_OK) rc = P->mem.alloc(&L.wf_hi, wn);
+        if (rc == IST_OK) rc = P->mem.alloc(&L.wf_lo, wn);
+        if (rc == IST_OK) rc = P->mem.alloc(&L.wd_hi, wn);
+        if (rc == IST_OK) rc = P->mem.alloc(&L.wd_lo, wn);
+        int TW, TH;
+        pick_tile(L.W, &TW, &TH);
+        const Layer& I = P->layers[l - 1];
+        if (rc == IST_OK) rc = map_act(&L.mA_hi, I.out.hi, batch, L.H, L.W, L.cin, TW, TH);
+        if (rc == IST_OK) rc = map_act(&L.mA_lo, I.out.lo, batch, L.H, L.W, L.cin, TW, TH);
+        if (rc == IST_OK) rc = map_b(&L.mBf_hi, L.wf_hi, 9, L.cout, L.cin, conv_n_tile(L.cout));
+        if (rc == IST_OK) rc = map_b(&L.mBf_lo, L.wf_lo, 9, L.cout, L.cin, conv_n_tile(L.cout));
+        if (rc == IST_OK) rc = map_b(&L.mBd_hi, L.wd_hi, 9, L.cin, L.cout, conv_n_tile(L.cin));
+        if (rc == IST_OK) rc = map_b(&L.mBd_lo, L.wd_lo, 9, L.cin, L.cout, conv_n_tile(L.cin));
+        if (rc == IST_OK) rc = map_act(&L.mG_hi, L.dY.hi, batch, L.H, L.W, L.cout, TW, TH);
+        if (rc == IST_OK) rc = map_act(&L.mG_lo, L.dY.lo, batch, L.H, L.W, L.cout, TW, TH);
+    }
+    if (rc != IST_OK) {
+        delete P;
+        return rc;
+    }
+    *out = P;
+    return IST_OK;
+}
+
+int ist_plan_destroy(ist_plan* plan) {
+    if (plan != nullptr) delete plan;
+    return IST_OK;
+}
+
+size_t ist_plan_bytes(const ist_plan* plan) { return plan != nullptr ? plan->mem.bytes : 0; }
+
+int ist_plan_set_weights(ist_plan* P, int conv_index, const float* w_dev, const float* b_dev, void* stream) {
+    if (P == nullptr || w_dev == nullptr || b_dev == nullptr) return fail(IST_ERR_ARG, "ist_plan_set_weights: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (Layer& L : P->layers) {
+        if (L.kind != IST_LAYER_CONV3X3_RELU || L.conv_index != conv_index) continue;
+        const size_t wn = (size_t)L.cout * L.cin * 9;
+        IST_CUDA(cudaMemcpyAsync(L.bias, b_dev, L.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (L.conv_index == 0) {
+            IST_CUDA(cudaMemcpyAsync(L.w_f32, w_dev, wn * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        } else {
+            // power-of-two scale so the largest |w| lands in [2^13, 2^14): both fp16 halves stay normal
+            std::vector<float> hw(wn);
+            IST_CUDA(cudaMemcpyAsync(hw.data(), w_dev, wn * sizeof(float), cudaMemcpyDeviceToHost, st));
+            IST_CUDA(cudaStreamSynchronize(st));
+            float mx = 0.f;
+            for (float v : hw) {
+                if (!(v == v) || v > 3e38f || v < -3e38f) return fail(IST_ERR_ARG, "conv %d: non-finite weight", conv_index);
+                const float a = v < 0 ? -v : v;
+                if (a > mx) mx = a;
+            }
+            int e = 0;
+            if (mx > 0.f) e = 13 - ilogbf(mx);
+            L.w_scale = ldexpf(1.f, e);
+            weight_repack_kernel<<<ew_grid(wn, 256), 256, 0, st>>>(w_dev, L.cout, L.cin, L.w_scale, L.wf_hi, L.wf_lo, L.wd_hi, L.wd_lo);
+            IST_CUDA(cudaGetLastError());
+        }
+        L.has_weights = true;
+        return IST_OK;
+    }
+    return fail(IST_ERR_ARG, "ist_plan_set_weights: no conv with index %d", conv_index);
+}
+
+int ist_plan_forward(ist_plan* P, const float* x_dev, int upto_layer, void* stream) {
+    if (P == nullptr || x_dev == nullptr) return fail(IST_ERR_ARG, "ist_plan_forward: null argument");
+    if (upto_layer < 0 || upto_layer >= (int)P->layers.size()) return fail(IST_ERR_ARG, "ist_plan_forward: layer %d out of range", upto_layer);
+    return run_forward(P, x_dev, upto_layer, (cudaStream_t)stream);
+}
+
+int ist_plan_feature_shape(const ist_plan* P, int layer, int* C, int* h, int* w) {
+    if (P == nullptr || layer < 0 || layer >= (int)P->layers.size()) return fail(IST_ERR_ARG, "ist_plan_feature_shape: bad layer");
+    const Layer& L = P->layers[layer];
+    if (C) *C = L.C;
+    if (h) *h = L.H;
+    if (w) *w = L.W;
+    return IST_OK;
+}
+
+int ist_plan_get_feature(ist_plan* P, int layer, float* out_dev, void* stream) {
+    if (P == nullptr || out_dev == nullptr || layer < 0 || layer >= (int)P->layers.size()) return fail(IST_ERR_ARG, "ist_plan_get_feature: bad argument");
+    if (layer > P->forwarded_upto) return fail(IST_ERR_STATE, "layer %d has not been computed (forward ran to %d)", layer, P->forwarded_upto);
+    const Layer& L = P->layers[layer];
+    const size_t items = L.out_elems / 2;
+    planes_to_nchw_kernel<false><<<ew_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(L.out.hi, L.out.lo, out_dev, P->NB, L.C,
+                                                                                      L.H * L.W, 1.f / kActScale);
+    IST_CUDA(cudaGetLastError());
+    return IST_OK;
+}
+
+int ist_plan_gram(ist_plan* P, int layer, float* out_dev, void* stream) {
+    if (P == nullptr || out_dev == nullptr || layer < 0 || layer >= (int)P->layers.size()) return fail(IST_ERR_ARG, "ist_plan_gram: bad argument");
+    if (layer > P->forwarded_upto) return fail(IST_ERR_STATE, "layer %d has not been computed", layer);
+    cudaStream_t st = (cudaStream_t)stream;
+    Layer& L = P->layers[layer];
+    IST_TRY(ensure_gram_buffers(P, L));
+    IST_TRY(run_gram_partial(P, L, st));
+    GramFinalizeParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.NB = P->NB; gp.n_layers = 1; gp.loss_stride = 0;
+    fill_gram_layer(P, L, &gp.L[0], out_dev, nullptr);
+    dim3 grid(GRAM_FIN_BLOCKS, 1, P->NB);
+    gram_reduce_kernel<<<grid, 256, 0, st>>>(gp);
+    IST_CUDA(cudaGetLastError());
+    return IST_OK;
+}
+
+int ist_plan_set_loss(ist_plan* P, int n_style, const int* style_layers, const float* style_weights, int n_content,
+                      const int* content_layers, const float* content_weights) {
+    if (P == nullptr || n_style < 0 || n_content < 0 || n_style > 8 || n_content > 4 || n_style + n_content > kMaxLoss)
+        return fail(IST_ERR_ARG, "ist_plan_set_loss: at most 8 style and 4 content layers");
+    for (Layer& L : P->layers) { L.style_slot = -1; L.content_slot = -1; }
+    P->style_layers.clear(); P->content_layers.clear();
+    for (int k = 0; k < n_style; ++k) {
+        const int l = style_layers[k];
+        if (l < 0 || l >= (int)P->layers.size() || P->layers[l].kind != IST_LAYER_CONV3X3_RELU) return fail(IST_ERR_ARG, "style layer %d must be a conv+relu layer of the plan", l);
+        Layer& L = P->layers[l];
+        if (L.style_slot >= 0) return fail(IST_ERR_ARG, "style layer %d listed twice", l);
+        L.style_slot = k; L.style_w = style_weights[k];
+        IST_TRY(ensure_gram_buffers(P, L));
+        P->style_layers.push_back(l);
+    }
+    for (int k = 0; k < n_content; ++k) {
+        const int l = content_layers[k];
+        if (l < 0 || l >= (int)P->layers.size() || P->layers[l].kind != IST_LAYER_CONV3X3_RELU) return fail(IST_ERR_ARG, "content layer %d must be a conv+relu layer of the plan", l);
+        Layer& L = P->layers[l];
+        if (L.content_slot >= 0) return fail(IST_ERR_ARG, "content layer %d listed twice", l);
+        L.content_slot = n_style + k; L.content_w = content_weights[k];
+        if (L.T.hi == nullptr) {
+            IST_TRY(alloc_planes(P->mem, &L.T, L.out_elems));
+            IST_TRY(P->mem.alloc(&L.c_partial, (size_t)P->NB * kContentBlocks));
+        }
+        P->content_layers.push_back(l);
+    }
+    P->n_style = n_style; P->n_content = n_content;
+    return IST_OK;
+}
+
+int ist_plan_set_style_target(ist_plan* P, int style_slot, const float* gram_dev, void* stream) {
+    if (P == nullptr || gram_dev == nullptr || style_slot < 0 || style_slot >= P->n_style) return fail(IST_ERR_ARG, "ist_plan_set_style_target: bad slot");
+    Layer& L = P->layers[P->style_layers[style_slot]];
+    IST_CUDA(cudaMemcpyAsync(L.target, gram_dev, (size_t)L.C * L.C * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    L.target_set = true;
+    return IST_OK;
+}
+
+int ist_plan_capture_content_target(ist_plan* P, int content_slot, void* stream) {
+    if (P == nullptr || content_slot < 0 || content_slot >= P->n_content) return fail(IST_ERR_ARG, "ist_plan_capture_content_target: bad slot");
+    const int l = P->content_layers[content_slot];
+    if (l > P->forwarded_upto) return fail(IST_ERR_STATE, "content layer %d has not been computed", l);
+    Layer& L = P->layers[l];
+    cudaStream_t st = (cudaStream_t)stream;
+    IST_CUDA(cudaMemcpyAsync(L.T.hi, L.out.hi, L.out_elems * 2, cudaMemcpyDeviceToDevice, st));
+    IST_CUDA(cudaMemcpyAsync(L.T.lo, L.out.lo, L.out_elems * 2, cudaMemcpyDeviceToDevice, st));
+    L.content_set = true;
+    return IST_OK;
+}
+
+int ist_plan_loss_and_grad(ist_plan* P, const float* x_dev, float* grad_dev, float* losses_dev, void* stream) {
+    if (P == nullptr || x_dev == nullptr || grad_dev == nullptr || losses_dev == nullptr) return fail(IST_ERR_ARG, "ist_plan_loss_and_grad: null argument");
+    const int deepest = deepest_loss_layer(P);
+    if (deepest < 0) return fail(IST_ERR_STATE, "no loss configured (ist_plan_set_loss)");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (Layer& L : P->layers) L.ext_active = false;
+    IST_TRY(run_forward(P, x_dev, deepest, st));
+    IST_TRY(run_losses(P, losses_dev, st));
+    Seeds S;
+    S.use_losses = true;
+    IST_TRY(run_backward(P, S, deepest, grad_dev, st));
+    return IST_OK;
+}
+
+int ist_plan_backward(ist_plan* P, int n_seeds, const int* layers, const float* const* seeds_dev, float* grad_dev, void* stream) {
+    if (P == nullptr || n_seeds < 1 || layers == nullptr || seeds_dev == nullptr || grad_dev == nullptr) return fail(IST_ERR_ARG, "ist_plan_backward: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (Layer& L : P->layers) L.ext_active = false;
+    int deepest = -1;
+    for (int i = 0; i < n_seeds; ++i) {
+        const int l = layers[i];
+        if (l < 0 || l > P->forwarded_upto) return fail(IST_ERR_STATE, "seed layer %d has not been computed by the last forward", l);
+        Layer& L = P->layers[l];
+        if (L.ext_active) return fail(IST_ERR_ARG, "seed layer %d listed twice", l);
+        if (L.ext_seed == nullptr) IST_TRY(P->mem.alloc(&L.ext_seed, L.out_elems));
+        nchw_to_nhwc_f32_kernel<<<ew_grid(L.out_elems, 256), 256, 0, st>>>(seeds_dev[i], L.ext_seed, P->NB, L.C, L.H * L.W);
+        IST_CUDA(cudaGetLastError());
+        L.ext_active = true;
+        if (l > deepest) deepest = l;
+    }
+    Seeds S;
+    S.use_losses = false;
+    int rc = run_backward(P, S, deepest, grad_dev, st);
+    for (Layer& L : P->layers) L.ext_active = false;
+    return rc;
+}
+
+}  // extern "C"
+
+// internal hooks for ist_lbfgs.cu / ist_ops.cu
+namespace ist {
+int plan_batch(const ist_plan* P) { return P->NB; }
+int plan_image_elems(const ist_plan* P) { return 3 * P->H * P->W; }
+int plan_n_losses(const ist_plan* P) { return P->n_style + P->n_content; }
+}  // namespace ist

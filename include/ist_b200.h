@@ -1,0 +1,123 @@
+/* ist_b200.h — C ABI of the B200-native Gatys style-transfer hot path.
+ *
+ * The reference (DJNing/Can-Image-Style-Transfer-Save-Automotive-Radar, IST/) has no FFI: its boundary is the
+ * Python plugin API  build_model -> meta_arch.VGG(cfg, pool) / GramMatrix / GramMSELoss / optimize().
+ * Each entry point below cites the reference interface it stands in for (paths relative to the reference
+ * root). The Python package `can-image-style-transfer-save-automotive-radar_b200` binds these with ctypes and
+ * mirrors the reference's classes on top.
+ *
+ * Conventions
+ *   - every pointer named *_dev is a CUDA device pointer owned by the caller (PyTorch allocator) and only
+ *     borrowed for the call; fp32, contiguous, NCHW for images/features (the reference layout), [C,C] for Grams;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream); all work is
+ *     enqueued on it, nothing synchronises unless stated;
+ *   - return value 0 = ok, non-zero = error (never throws across the ABI); ist_last_error() gives the text;
+ *   - there is no CPU fallback: without an sm_100 device every compute entry point returns IST_ERR_DEVICE;
+ *   - a plan is bound to one device and must not be used from two threads at once.
+ */
+#ifndef IST_B200_H_
+#define IST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IST_OK 0
+#define IST_ERR_ARG 1
+#define IST_ERR_CUDA 2
+#define IST_ERR_DEVICE 3
+#define IST_ERR_STATE 4
+
+#define IST_LAYER_CONV3X3_RELU 0 /* nn.Conv2d(k=3,pad=1) + F.relu, IST/model/meta_arch/vgg.py:13-16,52 */
+#define IST_LAYER_MAXPOOL2X2 1   /* nn.MaxPool2d(2,2),            IST/model/meta_arch/vgg.py:21-22,54 */
+
+typedef struct ist_plan ist_plan;
+
+typedef struct ist_layer_desc {
+    int kind;     /* IST_LAYER_* */
+    int cin;      /* conv only */
+    int cout;     /* conv only */
+} ist_layer_desc;
+
+/* library / device ------------------------------------------------------------------------------------- */
+const char* ist_last_error(void);
+int ist_version(void);
+/* 0 when the current CUDA device can run the kernels (compute capability 10.x), IST_ERR_DEVICE otherwise. */
+int ist_device_check(void);
+
+/* plan: VGG.__init__ (IST/model/meta_arch/vgg.py:6-42) for one (batch, H, W) ------------------------------ */
+/* layers[] follows cfg.MODEL.VGG.FORWARD_SEQ (IST/config/defaults.py:48-54) truncated at the deepest layer the
+ * caller will ever request. The first layer must be a conv with cin == 3; all other convs need cin, cout % 64 == 0. */
+int ist_plan_create(ist_plan** out, int n_layers, const ist_layer_desc* layers, int batch, int H, int W);
+int ist_plan_destroy(ist_plan* plan);
+/* vgg.load_state_dict (IST/main.py:30): weight OIHW [cout,cin,3,3], bias [cout]; copied and repacked, the caller
+ * keeps ownership. conv_index counts conv layers only (0 = conv1_1). */
+int ist_plan_set_weights(ist_plan* plan, int conv_index, const float* w_dev, const float* b_dev, void* stream);
+/* bytes of device memory held by the plan */
+size_t ist_plan_bytes(const ist_plan* plan);
+
+/* forward: VGG.forward(input, out_keys) (IST/model/meta_arch/vgg.py:44-58) ------------------------------- */
+/* runs layers [0, upto_layer] on x (fp32 NCHW [batch,3,H,W]); features stay inside the plan */
+int ist_plan_forward(ist_plan* plan, const float* x_dev, int upto_layer, void* stream);
+/* copy the output of `layer` (after ReLU / after pool) out as fp32 NCHW [batch,C,h,w] */
+int ist_plan_get_feature(ist_plan* plan, int layer, float* out_dev, void* stream);
+int ist_plan_feature_shape(const ist_plan* plan, int layer, int* C, int* h, int* w);
+/* GramMatrix.forward (IST/model/meta_arch/gram_matrix.py:6-11) of the current features of `layer`: out [batch,C,C] */
+int ist_plan_gram(ist_plan* plan, int layer, float* out_dev, void* stream);
+
+/* loss configuration: StyleTransfer(vgg, loss_layers, loss_functions, loss_weights) (IST/main.py:35-43) ---- */
+/* style layers use GramMSELoss (IST/model/meta_arch/gram_mse_loss.py:6-8), content layers nn.MSELoss
+ * (IST/main.py:36-37); loss k of the output vector is style[0..n_style) then content[0..n_content). */
+int ist_plan_set_loss(ist_plan* plan, int n_style, const int* style_layers, const float* style_weights,
+                      int n_content, const int* content_layers, const float* content_weights);
+/* targets (IST/model/engine/utils.py:19-20), cached in the plan until replaced */
+int ist_plan_set_style_target(ist_plan* plan, int style_slot, const float* gram_dev /*[C,C]*/, void* stream);
+/* content target of slot := current features of that layer (run ist_plan_forward on the content image first) */
+int ist_plan_capture_content_target(ist_plan* plan, int content_slot, void* stream);
+
+/* closure: IST/model/engine/utils.py:29-41 — forward, weighted layer losses, total, d(total)/dx -------------- */
+/* x, grad: fp32 NCHW [batch,3,H,W]; losses: [batch, n_style+n_content+1], last entry = sum in list order.
+ * Frames of a batch are independent problems (each is the reference's b = 1 case). */
+int ist_plan_loss_and_grad(ist_plan* plan, const float* x_dev, float* grad_dev, float* losses_dev, void* stream);
+
+/* generic backward for VGG.forward used under autograd with arbitrary downstream losses:
+ * seeds[i] = dL/d(output of layers[i]) as fp32 NCHW; requires a preceding ist_plan_forward on the same x. */
+int ist_plan_backward(ist_plan* plan, int n_seeds, const int* layers, const float* const* seeds_dev,
+                      float* grad_dev, void* stream);
+
+/* L-BFGS: torch.optim.LBFGS([x]) with the defaults the reference uses (IST/model/engine/utils.py:24,43) --- */
+typedef struct ist_lbfgs ist_lbfgs;
+int ist_lbfgs_create(ist_lbfgs** out, ist_plan* plan, int history_size, int max_iter, int max_eval, float lr,
+                     double tolerance_grad, double tolerance_change);
+int ist_lbfgs_destroy(ist_lbfgs* opt);
+/* one optimizer.step(closure) on x (updated in place); evals_out += closure evaluations performed;
+ * loss_out (host) = loss of the first closure call of this step, as LBFGS.step returns it. Synchronises once. */
+int ist_lbfgs_step(ist_lbfgs* opt, float* x_dev, int* evals_out, float* loss_out, void* stream);
+/* per-frame losses of the most recent closure evaluation: [batch, n_losses+1] */
+int ist_lbfgs_last_losses(ist_lbfgs* opt, float* losses_host);
+
+/* per-op entry points for unit parity (fp32 NCHW in/out, temporaries allocated inside) ---------------------- */
+int ist_op_conv3x3_relu_fwd(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev, int batch,
+                            int cin, int cout, int H, int W, int apply_relu, void* stream);
+int ist_op_conv3x3_dgrad(const float* dy_dev, const float* w_dev, float* dx_dev, int batch, int cin, int cout,
+                         int H, int W, int passes, void* stream);
+int ist_op_maxpool2x2_fwd(const float* x_dev, float* y_dev, int batch, int C, int H, int W, void* stream);
+int ist_op_maxpool2x2_bwd(const float* x_dev, const float* dy_dev, float* dx_dev, int batch, int C, int H, int W,
+                          void* stream);
+int ist_op_relu_bwd(const float* y_dev, const float* dy_dev, float* dx_dev, int batch, int C, int H, int W,
+                    void* stream);
+int ist_op_gram(const float* x_dev, float* g_dev, int batch, int C, int H, int W, void* stream);
+/* weight * mean((Gram(x) - target)^2) and its gradient w.r.t. x */
+int ist_op_gram_mse(const float* x_dev, const float* target_dev, float weight, float* loss_dev, float* dx_dev,
+                    int batch, int C, int H, int W, void* stream);
+/* weight * mean((x - t)^2) and its gradient w.r.t. x */
+int ist_op_mse(const float* x_dev, const float* t_dev, float weight, float* loss_dev, float* dx_dev, int batch,
+               int C, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IST_B200_H_ */
