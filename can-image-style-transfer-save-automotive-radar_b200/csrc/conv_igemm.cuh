@@ -8,14 +8,22 @@
 //   M = 128 output pixels (a TH x TW rectangle of one frame), N = N_TILE output channels,
 //   K = taps * Cin walked as (tap, 64-channel chunk).
 // Operands are NHWC 16-bit *planes*: every fp32 tensor is carried as hi + lo (two fp16 or two bf16
-// arrays) and each K step issues hi*hi, hi*lo, lo*hi into one fp32 TMEM accumulator ("3-pass split"),
-// which restores ~22 mantissa bits (the forward must be fp32-accurate or ReLU/pool masks flip).
+// arrays); each K step issues hi*hi, hi*lo and lo*hi ("3-pass split", ~22 operand mantissa bits;
+// the forward must be fp32-accurate or ReLU/pool masks flip).
 // Zero padding comes from TMA out-of-bounds fill: the A box is fetched at (x0 + kx - 1, y0 + ky - 1).
 // Every output pixel sees the same K order, so equal patches give bit-equal outputs.
 //
+// Accumulation. The tensor core adds into its fp32 accumulator with truncation, so one long accumulation
+// chain drifts by ~3e-8 per MMA (measured: rel. error 2e-6 at K=576 growing to 1.3e-5 at K=4608, see
+// profiles/r01_selftest_v1_single_accumulator.log). Therefore:
+//   * hi*hi products go to a *short* chain (p.promote k-steps = 4*promote MMAs) in one of two "main" TMEM
+//     buffers; the epilogue warps drain each finished chain into fp32 registers (round-to-nearest adds)
+//     while the tensor core fills the other buffer;
+//   * hi*lo + lo*hi (2^-11 smaller) run as one long chain in a separate "cross" TMEM buffer, whose
+//     truncation error is 2^-11 smaller as well, and are added once at the end of the tile.
+//
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> global), double-buffered accumulator so the epilogue of
-// tile i overlaps the MMAs of tile i+1. Persistent CTAs walk tiles round-robin (deterministic).
+// warps 2..5 = promotion + epilogue (TMEM -> registers -> global). Persistent CTAs walk tiles round-robin.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -33,6 +41,7 @@ struct ConvParams {
     int TW, TH;          // pixel tile, TW * TH == 128
     int tiles_x, tiles_y, tiles_n;
     int passes;          // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi only
+    int promote;         // k-steps (of 64 channels) per main accumulation chain, >= 1
     int b_frame;         // 1: third B coordinate is the frame (per-frame B, Gram backward), 0: the tap
     uint32_t idesc;
     int mode;
@@ -49,11 +58,11 @@ struct ConvParams {
     // CONV_GRAD extras: v = acc*alpha (+ addend) (+ content_coef * (F - T)); v = mask > 0 ? v : 0
     const float* addend;        // fp32 NHWC, same shape as the output
     const uint16_t* mask_hi;    // fp16 hi plane of the ReLU output the gradient flows into
-    const uint16_t* f_hi;       // content term: current feature planes (fp16, scaled by 1/f_inv_scale)
+    const uint16_t* f_hi;       // content term: current feature planes (fp16, scaled)
     const uint16_t* f_lo;
     const uint16_t* t_hi;       // content target planes (same scaling)
     const uint16_t* t_lo;
-    float content_coef;         // 2*w/(C*H*W) * f_inv_scale
+    float content_coef;         // 2*w/(C*H*W) / plane scale
 };
 
 template <int N_TILE>
@@ -61,8 +70,8 @@ struct ConvCfg {
     static constexpr int A_BYTES = 128 * 128;        // 128 pixels x 64 ch x 2 B
     static constexpr int B_BYTES = N_TILE * 128;     // N_TILE couts x 64 ch x 2 B
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = (N_TILE == 256) ? 2 : (N_TILE == 128 ? 3 : 4);
-    static constexpr int TMEM_COLS = (2 * N_TILE < 32) ? 32 : 2 * N_TILE;   // two accumulator buffers
+    static constexpr int STAGES = (N_TILE == 128 ? 3 : 4);
+    static constexpr int TMEM_COLS = 4 * N_TILE;     // main[2] + cross[2]
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
 };
@@ -80,6 +89,90 @@ __device__ __forceinline__ float h_hi_f(uint32_t u) { return __half2float(__usho
 __device__ __forceinline__ float bf_lo_f(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi_f(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
+// Epilogue for 32 consecutive output channels of one pixel; `o` = element offset of the first channel, `cb` = its
+// channel index (for the bias). v[] holds acc * alpha on entry.
+__device__ __forceinline__ void conv_epilogue_32(const ConvParams& p, float (&v)[32], size_t o, int cb) {
+    if (p.mode == CONV_FWD) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            const float a = fmaxf(v[j] + __ldg(p.bias + cb + j), 0.f) * p.out_scale;
+            const float b = fmaxf(v[j + 1] + __ldg(p.bias + cb + j + 1), 0.f) * p.out_scale;
+            const uint32_t h = pack_h2(a, b);
+            hi[j >> 1] = h;
+            lo[j >> 1] = pack_h2(a - h_lo_f(h), b - h_hi_f(h));
+        }
+        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
+        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            dh[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+            dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        }
+        return;
+    }
+    if (p.addend != nullptr) {
+        const float4* ad = reinterpret_cast<const float4*>(p.addend + o);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 t = __ldg(ad + q);
+            v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+        }
+    }
+    if (p.f_hi != nullptr) {
+        const uint4* fh = reinterpret_cast<const uint4*>(p.f_hi + o);
+        const uint4* fl = reinterpret_cast<const uint4*>(p.f_lo + o);
+        const uint4* th = reinterpret_cast<const uint4*>(p.t_hi + o);
+        const uint4* tl = reinterpret_cast<const uint4*>(p.t_lo + o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 a = __ldg(fh + q), b = __ldg(fl + q), c = __ldg(th + q), d = __ldg(tl + q);
+            const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
+            const uint32_t uc[4] = {c.x, c.y, c.z, c.w}, ud[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float d0 = (h_lo_f(ua[e]) - h_lo_f(uc[e])) + (h_lo_f(ub[e]) - h_lo_f(ud[e]));
+                const float d1 = (h_hi_f(ua[e]) - h_hi_f(uc[e])) + (h_hi_f(ub[e]) - h_hi_f(ud[e]));
+                v[8 * q + 2 * e] += p.content_coef * d0;
+                v[8 * q + 2 * e + 1] += p.content_coef * d1;
+            }
+        }
+    }
+    if (p.mask_hi != nullptr) {
+        const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 a = __ldg(mk + q);
+            const uint32_t ua[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (!(h_lo_f(ua[e]) > 0.f)) v[8 * q + 2 * e] = 0.f;
+                if (!(h_hi_f(ua[e]) > 0.f)) v[8 * q + 2 * e + 1] = 0.f;
+            }
+        }
+    }
+    if (p.out_f32 != nullptr) {
+        float4* d = reinterpret_cast<float4*>(p.out_f32 + o);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            const uint32_t h = pack_bf2(v[j], v[j + 1]);
+            hi[j >> 1] = h;
+            lo[j >> 1] = pack_bf2(v[j] - bf_lo_f(h), v[j + 1] - bf_hi_f(h));
+        }
+        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
+        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            dh[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+            dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        }
+    }
+}
+
 template <int N_TILE>
 __global__ void __launch_bounds__(192, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -90,14 +183,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-    // barrier map: full[s] @ 8*s, empty[s] @ 64 + 8*s, tfull[a] @ 128 + 8*a, tempty[a] @ 144 + 8*a, tmem ptr @ 160
+    // barrier map (8 B each): full[s] @0, empty[s] @64, main_full[2] @128, main_empty[2] @144,
+    // cross_full[2] @160, cross_empty[2] @176, tmem base address @192
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
-    auto tfull_bar = [&](int a) { return bar_base + 128u + 8u * a; };
-    auto tempty_bar = [&](int a) { return bar_base + 144u + 8u * a; };
-    const uint32_t tmem_slot = bar_base + 160u;
-    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 160);
+    auto mfull_bar = [&](uint32_t b) { return bar_base + 128u + 8u * b; };
+    auto mempty_bar = [&](uint32_t b) { return bar_base + 144u + 8u * b; };
+    auto xfull_bar = [&](uint32_t a) { return bar_base + 160u + 8u * a; };
+    auto xempty_bar = [&](uint32_t a) { return bar_base + 176u + 8u * a; };
+    const uint32_t tmem_slot = bar_base + 192u;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
+        smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * Cfg::STAGE_BYTES + 192);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -113,9 +209,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 128);
+        for (uint32_t a = 0; a < 2; ++a) {
+            mbar_init(mfull_bar(a), 1);
+            mbar_init(mempty_bar(a), 128);
+            mbar_init(xfull_bar(a), 1);
+            mbar_init(xempty_bar(a), 128);
         }
         fence_barrier_init();
     }
@@ -129,7 +227,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     const int total_tiles = tiles_m * p.tiles_n;
     const int cchunks = p.Cin >> 6;
     const int kiters = p.taps * cchunks;
-    const uint32_t stage_tx = (p.passes == 3) ? (uint32_t)Cfg::STAGE_BYTES : (uint32_t)(Cfg::A_BYTES + Cfg::B_BYTES);
+    const int promote = p.promote < 1 ? 1 : p.promote;
+    const bool split = (p.passes == 3);
+    const uint32_t stage_tx = split ? (uint32_t)Cfg::STAGE_BYTES : (uint32_t)(Cfg::A_BYTES + Cfg::B_BYTES);
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer ------------------------------------------------
@@ -151,15 +251,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         dy = tap / 3 - 1;
                         dx = tap % 3 - 1;
                     }
+                    const int bz = p.b_frame ? fr : tap;
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sB = sA + 2 * Cfg::A_BYTES;
                     mbar_arrive_expect_tx(full_bar(stage), stage_tx);
                     tma_load_4d(sA, &tmA_hi, full_bar(stage), cc * 64, x0 + dx, y0 + dy, fr);
-                    tma_load_3d(sB, &tmB_hi, full_bar(stage), cc * 64, n0, p.b_frame ? fr : tap);
-                    if (p.passes == 3) {
+                    tma_load_3d(sB, &tmB_hi, full_bar(stage), cc * 64, n0, bz);
+                    if (split) {
                         tma_load_4d(sA + Cfg::A_BYTES, &tmA_lo, full_bar(stage), cc * 64, x0 + dx, y0 + dy, fr);
-                        tma_load_3d(sB + Cfg::B_BYTES, &tmB_lo, full_bar(stage), cc * 64, n0, p.b_frame ? fr : tap);
+                        tma_load_3d(sB + Cfg::B_BYTES, &tmB_lo, full_bar(stage), cc * 64, n0, bz);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -169,159 +270,117 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         // ------------------------------------------------ MMA issuer --------------------------------------------------
         int stage = 0;
         uint32_t phase = 0;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
+        uint32_t mcount = 0;     // main chains issued so far (ring of 2 buffers)
+        uint32_t tcount = 0;     // tiles issued so far (ring of 2 cross buffers)
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const uint32_t xa = tcount & 1u;
+            const uint32_t d_cross = tmem_base + (uint32_t)(2 * N_TILE) + xa * N_TILE;
+            if (split) {
+                mbar_wait(xempty_bar(xa), ((tcount >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+            }
             for (int kit = 0; kit < kiters; ++kit) {
+                const int in_chain = kit % promote;
+                const uint32_t mb = mcount & 1u;
+                if (in_chain == 0) {
+                    mbar_wait(mempty_bar(mb), ((mcount >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                }
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 if (lane == 0) {
+                    const uint32_t d_main = tmem_base + mb * N_TILE;
                     const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sB = sA + 2 * Cfg::A_BYTES;
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
                         const uint64_t a_hi = umma_smem_desc_sw128(sA + k4 * 32, 0, 1024);
                         const uint64_t b_hi = umma_smem_desc_sw128(sB + k4 * 32, 0, 1024);
-                        umma_f16(d_tmem, a_hi, b_hi, p.idesc, (kit | k4) != 0 ? 1u : 0u);
-                        if (p.passes == 3) {
+                        umma_f16(d_main, a_hi, b_hi, p.idesc, (in_chain | k4) != 0 ? 1u : 0u);
+                    }
+                    const bool chain_end = (in_chain == promote - 1) || (kit == kiters - 1);
+                    if (chain_end) umma_commit(mfull_bar(mb));
+                    if (split) {
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const uint64_t a_hi = umma_smem_desc_sw128(sA + k4 * 32, 0, 1024);
+                            const uint64_t b_hi = umma_smem_desc_sw128(sB + k4 * 32, 0, 1024);
                             const uint64_t a_lo = umma_smem_desc_sw128(sA + Cfg::A_BYTES + k4 * 32, 0, 1024);
                             const uint64_t b_lo = umma_smem_desc_sw128(sB + Cfg::B_BYTES + k4 * 32, 0, 1024);
-                            umma_f16(d_tmem, a_hi, b_lo, p.idesc, 1u);
-                            umma_f16(d_tmem, a_lo, b_hi, p.idesc, 1u);
+                            umma_f16(d_cross, a_hi, b_lo, p.idesc, (kit | k4) != 0 ? 1u : 0u);
+                            umma_f16(d_cross, a_lo, b_hi, p.idesc, 1u);
                         }
                     }
                     umma_commit(empty_bar(stage));
-                    if (kit == kiters - 1) { umma_commit(tfull_bar(acc)); }
+                    if (split && kit == kiters - 1) umma_commit(xfull_bar(xa));
                 }
                 __syncwarp();
+                if (in_chain == promote - 1 || kit == kiters - 1) ++mcount;
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
-            acc ^= 1;
-            if (acc == 0) { acc_phase ^= 1u; }
         }
     } else {
-        // ------------------------------------------------ epilogue ----------------------------------------------------
+        // ------------------------------------------- promotion + epilogue ---------------------------------------------
         const int quad = warp & 3;              // TMEM lane quadrant this warp may read
         const int m = quad * 32 + lane;         // accumulator row == pixel inside the tile
         const int px = m % p.TW, py = m / p.TW;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int nchains = (kiters + promote - 1) / promote;
+        uint32_t mcount = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            float acc[N_TILE];
+#pragma unroll
+            for (int j = 0; j < N_TILE; ++j) acc[j] = 0.f;
+            for (int ch = 0; ch < nchains; ++ch, ++mcount) {
+                const uint32_t mb = mcount & 1u;
+                mbar_wait(mfull_bar(mb), (mcount >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(lane_base + mb * N_TILE + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+                }
+                tc_fence_before();
+                mbar_arrive(mempty_bar(mb));
+            }
+            if (split) {
+                const uint32_t xa = tcount & 1u;
+                mbar_wait(xfull_bar(xa), (tcount >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(lane_base + (uint32_t)(2 * N_TILE) + xa * N_TILE + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+                }
+                tc_fence_before();
+                mbar_arrive(xempty_bar(xa));
+            }
+            // final epilogue from registers
             const int tm = tile % tiles_m;
             const int tn = tile / tiles_m;
             const int tx = tm % p.tiles_x;
             const int ty = (tm / p.tiles_x) % p.tiles_y;
             const int fr = tm / (p.tiles_x * p.tiles_y);
             const int x = tx * p.TW + px, y = ty * p.TH + py, n0 = tn * N_TILE;
-            const bool valid = (x < p.W) && (y < p.H);
-            const size_t pix = ((size_t)fr * p.H + y) * p.W + x;
-            const size_t obase = pix * (size_t)p.Cout + n0;
-            float alpha = p.alpha;
-            if (p.alpha_dev != nullptr) { alpha *= __ldg(p.alpha_dev + (size_t)p.alpha_stride * fr); }
-
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N_TILE);
-#pragma unroll 1
-            for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(t_row + c0, r);
-                tmem_ld_wait();
-                if (valid) {
+            if ((x < p.W) && (y < p.H)) {
+                const size_t pix = ((size_t)fr * p.H + y) * p.W + x;
+                const size_t obase = pix * (size_t)p.Cout + n0;
+                float alpha = p.alpha;
+                if (p.alpha_dev != nullptr) alpha *= __ldg(p.alpha_dev + (size_t)p.alpha_stride * fr);
+#pragma unroll
+                for (int c0 = 0; c0 < N_TILE; c0 += 32) {
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r[j]) * alpha; }
-                    const size_t o = obase + c0;
-                    if (p.mode == CONV_FWD) {
-                        uint32_t hi[16], lo[16];
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            float a = fmaxf(v[j] + __ldg(p.bias + n0 + c0 + j), 0.f) * p.out_scale;
-                            float b = fmaxf(v[j + 1] + __ldg(p.bias + n0 + c0 + j + 1), 0.f) * p.out_scale;
-                            uint32_t h = pack_h2(a, b);
-                            hi[j >> 1] = h;
-                            lo[j >> 1] = pack_h2(a - h_lo_f(h), b - h_hi_f(h));
-                        }
-                        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
-                        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            dh[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-                            dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-                        }
-                    } else {
-                        if (p.addend != nullptr) {
-                            const float4* ad = reinterpret_cast<const float4*>(p.addend + o);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                float4 t = __ldg(ad + q);
-                                v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
-                            }
-                        }
-                        if (p.f_hi != nullptr) {
-                            const uint4* fh = reinterpret_cast<const uint4*>(p.f_hi + o);
-                            const uint4* fl = reinterpret_cast<const uint4*>(p.f_lo + o);
-                            const uint4* th = reinterpret_cast<const uint4*>(p.t_hi + o);
-                            const uint4* tl = reinterpret_cast<const uint4*>(p.t_lo + o);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 a = __ldg(fh + q), b = __ldg(fl + q), c = __ldg(th + q), d = __ldg(tl + q);
-                                const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
-                                const uint32_t uc[4] = {c.x, c.y, c.z, c.w}, ud[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    float d0 = (h_lo_f(ua[e]) - h_lo_f(uc[e])) + (h_lo_f(ub[e]) - h_lo_f(ud[e]));
-                                    float d1 = (h_hi_f(ua[e]) - h_hi_f(uc[e])) + (h_hi_f(ub[e]) - h_hi_f(ud[e]));
-                                    v[8 * q + 2 * e] += p.content_coef * d0;
-                                    v[8 * q + 2 * e + 1] += p.content_coef * d1;
-                                }
-                            }
-                        }
-                        if (p.mask_hi != nullptr) {
-                            const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + o);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 a = __ldg(mk + q);
-                                const uint32_t ua[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    if (!(h_lo_f(ua[e]) > 0.f)) v[8 * q + 2 * e] = 0.f;
-                                    if (!(h_hi_f(ua[e]) > 0.f)) v[8 * q + 2 * e + 1] = 0.f;
-                                }
-                            }
-                        }
-                        if (p.out_f32 != nullptr) {
-                            float4* d = reinterpret_cast<float4*>(p.out_f32 + o);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                            }
-                        } else {
-                            uint32_t hi[16], lo[16];
-#pragma unroll
-                            for (int j = 0; j < 32; j += 2) {
-                                uint32_t h = pack_bf2(v[j], v[j + 1]);
-                                hi[j >> 1] = h;
-                                lo[j >> 1] = pack_bf2(v[j] - bf_lo_f(h), v[j + 1] - bf_hi_f(h));
-                            }
-                            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
-                            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                dh[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-                                dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-                            }
-                        }
-                    }
+                    for (int j = 0; j < 32; ++j) v[j] = acc[c0 + j] * alpha;
+                    conv_epilogue_32(p, v, obase + c0, n0 + c0);
                 }
             }
-            tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
-            acc ^= 1;
-            if (acc == 0) { acc_phase ^= 1u; }
         }
     }
 

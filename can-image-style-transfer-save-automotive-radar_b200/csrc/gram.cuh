@@ -8,7 +8,9 @@
 // Only tiles with n_tile >= m_tile are computed (SYRK); gram_finalize mirrors them. Diagonal tiles reuse
 // the A tile as B (no second load). Split over pixels gives >= 1 CTA per SM even for C = 64; partial
 // results go to a [split] array that gram_finalize sums in a fixed order (deterministic, no atomics).
-// 3-pass split (hi*hi + hi*lo + lo*hi) as in conv_igemm.cuh.
+// 3-pass split (hi*hi + hi*lo + lo*hi) and the short-chain / register-promotion accumulation scheme of
+// conv_igemm.cuh (the tensor core truncates when it adds into its accumulator; Gram sums are all-positive, so a
+// long chain would be biased low by ~3e-8 per MMA).
 #pragma once
 #include "ptx.cuh"
 
@@ -21,6 +23,7 @@ struct GramParams {
     int splits;            // pixel splits per frame
     int chunks_per_split;  // 64-pixel chunks per split
     int passes;
+    int promote;           // 64-pixel k-steps per main accumulation chain
     uint32_t idesc;        // M = 128, N = n_tile, both MN-major
     float* partial;        // [NB][splits][C][C]
 };
@@ -29,7 +32,7 @@ struct GramCfg {
     static constexpr int T_BYTES = 128 * 128;            // [64 pixels][128 channels] x 2 B, as two 8 KB channel groups
     static constexpr int STAGE_BYTES = 4 * T_BYTES;      // A_hi, A_lo, B_hi, B_lo
     static constexpr int STAGES = 3;
-    static constexpr int TMEM_COLS = 128;
+    static constexpr int TMEM_COLS = 512;                // main[2] @0,128; cross @256
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
 };
 
@@ -43,10 +46,12 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
-    const uint32_t tfull_bar = bar_base + 128u;
-    const uint32_t tmem_slot = bar_base + 160u;
+    auto mfull_bar = [&](uint32_t b) { return bar_base + 128u + 8u * b; };
+    auto mempty_bar = [&](uint32_t b) { return bar_base + 144u + 8u * b; };
+    const uint32_t xfull_bar = bar_base + 160u;
+    const uint32_t tmem_slot = bar_base + 192u;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
-        smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * Cfg::STAGE_BYTES + 160);
+        smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * Cfg::STAGE_BYTES + 192);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -70,6 +75,7 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const int kiters = c_end > c_begin ? c_end - c_begin : 0;
     const int groups_a = (p.C >= 128) ? 2 : 1;           // 64-channel groups actually loaded per operand
     const int groups_b = p.n_tile >> 6;
+    const int promote = p.promote < 1 ? 1 : p.promote;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_hi);
@@ -78,7 +84,11 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(tfull_bar, 1);
+        for (uint32_t b = 0; b < 2; ++b) {
+            mbar_init(mfull_bar(b), 1);
+            mbar_init(mempty_bar(b), 128);
+        }
+        mbar_init(xfull_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc<Cfg::TMEM_COLS>(tmem_slot); }
@@ -113,28 +123,45 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     } else if (warp == 1) {
         int stage = 0;
         uint32_t phase = 0;
+        uint32_t mcount = 0;
+        const bool split3 = (p.passes == 3);
         for (int kit = 0; kit < kiters; ++kit) {
+            const int in_chain = kit % promote;
+            const uint32_t mb = mcount & 1u;
+            if (in_chain == 0) {
+                mbar_wait(mempty_bar(mb), ((mcount >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+            }
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
                 const uint32_t sB = diag ? sA : sA + 2 * Cfg::T_BYTES;
+                const uint32_t d_main = tmem_base + mb * 128u;
+                const uint32_t d_cross = tmem_base + 256u;
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {          // 16 pixels per MMA = two 8-row groups = 2048 B
                     const uint64_t a_hi = umma_smem_desc_sw128(sA + k4 * 2048, 8192, 1024);
                     const uint64_t b_hi = umma_smem_desc_sw128(sB + k4 * 2048, 8192, 1024);
-                    umma_f16(tmem_base, a_hi, b_hi, p.idesc, (kit | k4) != 0 ? 1u : 0u);
-                    if (p.passes == 3) {
+                    umma_f16(d_main, a_hi, b_hi, p.idesc, (in_chain | k4) != 0 ? 1u : 0u);
+                }
+                if (in_chain == promote - 1 || kit == kiters - 1) umma_commit(mfull_bar(mb));
+                if (split3) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const uint64_t a_hi = umma_smem_desc_sw128(sA + k4 * 2048, 8192, 1024);
+                        const uint64_t b_hi = umma_smem_desc_sw128(sB + k4 * 2048, 8192, 1024);
                         const uint64_t a_lo = umma_smem_desc_sw128(sA + Cfg::T_BYTES + k4 * 2048, 8192, 1024);
                         const uint64_t b_lo = umma_smem_desc_sw128(sB + Cfg::T_BYTES + k4 * 2048, 8192, 1024);
-                        umma_f16(tmem_base, a_hi, b_lo, p.idesc, 1u);
-                        umma_f16(tmem_base, a_lo, b_hi, p.idesc, 1u);
+                        umma_f16(d_cross, a_hi, b_lo, p.idesc, (kit | k4) != 0 ? 1u : 0u);
+                        umma_f16(d_cross, a_lo, b_hi, p.idesc, 1u);
                     }
                 }
                 umma_commit(empty_bar(stage));
-                if (kit == kiters - 1) { umma_commit(tfull_bar); }
+                if (split3 && kit == kiters - 1) umma_commit(xfull_bar);
             }
             __syncwarp();
+            if (in_chain == promote - 1 || kit == kiters - 1) ++mcount;
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
     } else {
@@ -142,27 +169,51 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         const int c1 = mt * 128 + quad * 32 + lane;
         const bool valid = (quad * 32 + lane) < (p.C >= 128 ? 128 : 64) && c1 < p.C;
         float* dst = p.partial + (((size_t)fr * p.splits + split) * p.C + (valid ? c1 : 0)) * (size_t)p.C + nt * 128;
-        if (kiters > 0) {
-            mbar_wait(tfull_bar, 0);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int nchains = (kiters + promote - 1) / promote;
+        float acc[128];
+#pragma unroll
+        for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+        for (int ch = 0; ch < nchains; ++ch) {
+            const uint32_t mb = (uint32_t)ch & 1u;
+            mbar_wait(mfull_bar(mb), ((uint32_t)ch >> 1) & 1u);
             tc_fence_after();
-        }
-        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-            uint32_t r[32];
-            if (kiters > 0) {
-                tmem_ld_32x32(t_row + c0, r);
-                tmem_ld_wait();
-            } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                if (c0 < p.n_tile) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(lane_base + mb * 128u + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+                }
             }
-            if (valid) {
-                float4* d = reinterpret_cast<float4*>(dst + c0);
+            tc_fence_before();
+            mbar_arrive(mempty_bar(mb));
+        }
+        if (p.passes == 3 && kiters > 0) {
+            mbar_wait(xfull_bar, 0);
+            tc_fence_after();
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    d[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                       __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                if (c0 < p.n_tile) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(lane_base + 256u + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+                }
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                if (c0 < p.n_tile) {
+                    float4* d = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        d[q] = make_float4(acc[c0 + 4 * q], acc[c0 + 4 * q + 1], acc[c0 + 4 * q + 2], acc[c0 + 4 * q + 3]);
+                }
             }
         }
     }

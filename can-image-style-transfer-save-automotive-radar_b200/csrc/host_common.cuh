@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -130,6 +131,15 @@ inline int launch_conv_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
     return IST_OK;
 }
 inline int conv_n_tile(int cout) { return cout >= 128 ? 128 : 64; }
+// k-steps per tensor-core accumulation chain before promotion to fp32 registers (IST_B200_PROMOTE overrides; 1 = most accurate)
+inline int promote_steps() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("IST_B200_PROMOTE");
+        v = (e != nullptr && atoi(e) > 0) ? atoi(e) : 1;
+    }
+    return v;
+}
 // Fills the tiling fields of p (NB,H,W,Cin,Cout,taps,passes,mode and epilogue pointers must be set) and launches.
 inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                        const CUtensorMap& b_lo, ConvParams p, bool bf16) {
@@ -139,6 +149,7 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
     p.tiles_y = (p.H + p.TH - 1) / p.TH;
     const int nt = conv_n_tile(p.Cout);
     p.tiles_n = p.Cout / nt;
+    if (p.promote < 1) p.promote = promote_steps();
     p.idesc = umma_idesc_f16(bf16 ? UMMA_FMT_BF16 : UMMA_FMT_F16, 128, nt, 0, 0);
     return nt == 128 ? launch_conv_t<128>(st, a_hi, a_lo, b_hi, b_lo, p) : launch_conv_t<64>(st, a_hi, a_lo, b_hi, b_lo, p);
 }
@@ -170,6 +181,7 @@ inline int launch_gram(cudaStream_t st, const CUtensorMap& m_hi, const CUtensorM
     p.splits = splits;
     p.chunks_per_split = chunks_per_split;
     p.passes = passes;
+    p.promote = promote_steps();
     p.idesc = umma_idesc_f16(UMMA_FMT_F16, 128, p.n_tile, 1, 1);
     p.partial = partial;
     const int tri = p.tiles_c * (p.tiles_c + 1) / 2;
