@@ -88,6 +88,7 @@ SIGNATURES = {
     "ist_op_maxpool2x2_bwd": (ctypes.c_int, [_vp, _vp, _vp] + [ctypes.c_int] * 4 + [_vp]),
     "ist_op_relu_bwd": (ctypes.c_int, [_vp, _vp, _vp] + [ctypes.c_int] * 4 + [_vp]),
     "ist_op_gram": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 4 + [_vp]),
+    "ist_op_gram_bwd": (ctypes.c_int, [_vp, _vp, _vp] + [ctypes.c_int] * 4 + [_vp]),
     "ist_op_gram_mse": (ctypes.c_int, [_vp, _vp, ctypes.c_float, _vp, _vp] + [ctypes.c_int] * 4 + [_vp]),
     "ist_op_mse": (ctypes.c_int, [_vp, _vp, ctypes.c_float, _vp, _vp] + [ctypes.c_int] * 4 + [_vp]),
 }

@@ -188,8 +188,24 @@ int ist_op_relu_bwd(const float* yv, const float* dy, float* dx, int NB, int C, 
     return route_op(yv, nullptr, dy, dx, NB, C, H, W, 1, (cudaStream_t)stream);
 }
 
+// |dG| block maxima for the scaling step of gram_dmat_kernel when dG comes from the caller
+__global__ void __launch_bounds__(256) absmax_blocks_kernel(const float* __restrict__ v, size_t n_per_frame, float* __restrict__ blk_max,
+                                                            float* __restrict__ blk_sum) {
+    __shared__ float sh[8];
+    const int fr = blockIdx.y;
+    float mx = 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_per_frame; i += (size_t)gridDim.x * blockDim.x)
+        mx = fmaxf(mx, fabsf(v[(size_t)fr * n_per_frame + i]));
+    mx = block_reduce_256<true>(mx, sh);
+    if (threadIdx.x == 0) {
+        blk_max[(size_t)fr * GRAM_FIN_BLOCKS + blockIdx.x] = mx;
+        blk_sum[(size_t)fr * GRAM_FIN_BLOCKS + blockIdx.x] = 0.f;
+    }
+}
+
+// target != nullptr: GramMSE loss + gradient; g_out != nullptr: Gram only; dg != nullptr: dx = (dG + dG^T) F / (H*W)
 static int gram_common(const float* x, const float* target, float weight, float* g_out, float* loss_out, float* dx, int NB,
-                       int C, int H, int W, cudaStream_t st) {
+                       int C, int H, int W, cudaStream_t st, const float* dg = nullptr) {
     Tmp t(st);
     const int HW = H * W;
     const size_t CC = (size_t)C * C;
@@ -208,7 +224,9 @@ static int gram_common(const float* x, const float* target, float weight, float*
     CUtensorMap g_hi, g_lo;
     IST_TRY(map_gram(&g_hi, fh, NB, HW, C));
     IST_TRY(map_gram(&g_lo, fl, NB, HW, C));
-    IST_TRY(launch_gram(st, g_hi, g_lo, NB, HW, C, splits, cps, partial, 3));
+    if (dg == nullptr) IST_TRY(launch_gram(st, g_hi, g_lo, NB, HW, C, splits, cps, partial, 3));
+    float* dummy_loss = nullptr;
+    if (dg != nullptr) IST_TRY(t.alloc(&dummy_loss, (size_t)NB));
     GramFinalizeParams gp;
     memset(&gp, 0, sizeof(gp));
     gp.NB = NB; gp.n_layers = 1; gp.loss_stride = 1;
@@ -219,9 +237,18 @@ static int gram_common(const float* x, const float* target, float weight, float*
     L.weight = weight;
     L.bwd_coef = (float)(2.0 * weight / ((double)C * C * HW * kS));
     dim3 grid(GRAM_FIN_BLOCKS, 1, NB);
-    gram_reduce_kernel<<<grid, 256, 0, st>>>(gp);
-    IST_CUDA(cudaGetLastError());
-    if (g_out != nullptr) return IST_OK;
+    if (dg == nullptr) {
+        gram_reduce_kernel<<<grid, 256, 0, st>>>(gp);
+        IST_CUDA(cudaGetLastError());
+        if (g_out != nullptr) return IST_OK;
+    } else {
+        IST_CUDA(cudaMemcpyAsync(diff, dg, (size_t)NB * CC * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        absmax_blocks_kernel<<<dim3(GRAM_FIN_BLOCKS, NB), 256, 0, st>>>(diff, CC, bm, bs);
+        IST_CUDA(cudaGetLastError());
+        gp.L[0].loss_out = dummy_loss;
+        gp.L[0].weight = 0.f;
+        gp.L[0].bwd_coef = (float)(1.0 / ((double)HW * kS));
+    }
     gram_dmat_kernel<<<grid, 256, 0, st>>>(gp);
     IST_CUDA(cudaGetLastError());
     IST_TRY(t.alloc(&o32, (size_t)NB * HW * C));
@@ -246,6 +273,12 @@ int ist_op_gram(const float* x, float* g, int NB, int C, int H, int W, void* str
     IST_TRY(dev_ok());
     if (x == nullptr || g == nullptr) return fail(IST_ERR_ARG, "ist_op_gram: null argument");
     return gram_common(x, nullptr, 0.f, g, nullptr, nullptr, NB, C, H, W, (cudaStream_t)stream);
+}
+
+int ist_op_gram_bwd(const float* x, const float* dg, float* dx, int NB, int C, int H, int W, void* stream) {
+    IST_TRY(dev_ok());
+    if (x == nullptr || dg == nullptr || dx == nullptr) return fail(IST_ERR_ARG, "ist_op_gram_bwd: null argument");
+    return gram_common(x, nullptr, 0.f, nullptr, nullptr, dx, NB, C, H, W, (cudaStream_t)stream, dg);
 }
 
 int ist_op_gram_mse(const float* x, const float* target, float weight, float* loss, float* dx, int NB, int C, int H, int W,

@@ -1,0 +1,130 @@
+"""Entry point with the reference's functions (IST/main.py:23-248): get_model, transfer_style and the batch-of-frames
+driver. Differences, all on the host side: `--config-file` is honoured (the reference parses and ignores it,
+main.py:103-116), data locations are arguments instead of hard-coded /home/dj paths (main.py:119,142-143), and when
+launched under torchrun the sorted frame list is sharded round-robin over the GPUs with one final gather.
+
+    python -m ist_b200.main --content-dir radar/ --style-img lidar/09033.png --output-dir out/
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 -m ist_b200.main --content-dir ... --style-img ...
+"""
+import argparse
+import glob
+import os
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+from PIL import Image
+
+from .config import get_cfg_defaults
+from .model import build_model
+from .model.engine import do_transfer_style
+from .model.engine.hr_transfer_style import do_hr_transfer_style
+from .model.meta_arch import GramMSELoss, StyleTransfer
+from .parallel import gather_frames, init_distributed, shard_indices
+from .util.logger import setup_logger
+
+
+def get_model(cfg, state_dict=None):
+    """main.py:23-44. `state_dict` overrides cfg.MODEL.WEIGHTS (there is no network here to fetch vgg_conv.pth)."""
+    vgg_model = build_model(cfg)
+    device = torch.device(cfg.MODEL.DEVICE)
+    vgg_model.to(device)
+    if state_dict is None:
+        if not os.path.exists(cfg.MODEL.WEIGHTS):
+            raise FileNotFoundError(f"{cfg.MODEL.WEIGHTS} not found: place vgg_conv.pth there (IST/util/download_models.sh) "
+                                    "or pass a state_dict")
+        state_dict = torch.load(cfg.MODEL.WEIGHTS, map_location="cpu")
+    vgg_model.load_state_dict(state_dict)
+    for param in vgg_model.parameters():
+        param.requires_grad = False
+
+    loss_layers = cfg.LOSS.STYLE_LAYERS + cfg.LOSS.CONTENT_LAYERS
+    loss_functions = [GramMSELoss()] * len(cfg.LOSS.STYLE_LAYERS) + [nn.MSELoss()] * len(cfg.LOSS.CONTENT_LAYERS)
+    loss_functions = [loss_function.to(device) for loss_function in loss_functions]
+    loss_weights = cfg.LOSS.STYLE_WEIGHTS + cfg.LOSS.CONTENT_WEIGHTS
+
+    model = StyleTransfer(vgg_model, loss_layers, loss_functions, loss_weights)
+    return model, device
+
+
+def transfer_style(cfg, high_resolution=False, state_dict=None):
+    """main.py:47-75: one content / style pair from the config; optional coarse-to-fine second stage."""
+    model, device = get_model(cfg, state_dict)
+    content_image = Image.open(cfg.DATA.CONTENT_IMG_PATH)
+    style_image = Image.open(cfg.DATA.STYLE_IMG_PATH)
+    out_image = do_transfer_style(cfg, model, content_image, style_image, device)
+    if high_resolution:
+        out_image = do_hr_transfer_style(cfg, model, content_image, style_image, out_image, device)
+    return out_image
+
+
+def transfer_style_schedule(cfg, sizes, state_dict=None):
+    """Coarse-to-fine schedule over several sizes, e.g. [512, 1024, 2048]: the reference's single hr stage
+    (hr_transfer_style.py:11-33) applied once per extra size, each hand-off through the 8-bit clamped image."""
+    model, device = get_model(cfg, state_dict)
+    content_image = Image.open(cfg.DATA.CONTENT_IMG_PATH)
+    style_image = Image.open(cfg.DATA.STYLE_IMG_PATH)
+    cfg = cfg.clone()
+    cfg.DATA.IMG_SIZE = sizes[0]
+    out_image = do_transfer_style(cfg, model, content_image, style_image, device)
+    for s in sizes[1:]:
+        cfg.HRDATA.IMG_SIZE = s
+        out_image = do_hr_transfer_style(cfg, model, content_image, style_image, out_image, device)
+    return out_image
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(description="PyTorch Style Transfer -- Content and Style Reconstruction (B200 path)")
+    parser.add_argument("--config-file", default="", metavar="FILE", help="path to config file", type=str)
+    parser.add_argument("--content-dir", default="", help="directory of content (radar) frames, *.png")
+    parser.add_argument("--style-img", default="", help="the shared style (lidar) image")
+    parser.add_argument("--output-dir", default="./output/full_transfer/", help="where the stylised frames go")
+    parser.add_argument("--max-frames", type=int, default=0, help="process at most this many frames (0 = all)")
+    parser.add_argument("--high-resolution", action="store_true", help="run the coarse-to-fine second stage")
+    parser.add_argument("opts", help="Modify config options using the command-line", default=None, nargs=argparse.REMAINDER)
+    args = parser.parse_args(argv)
+
+    cfg = get_cfg_defaults()
+    if args.config_file:
+        cfg.merge_from_file(args.config_file)
+    if args.opts:
+        cfg.merge_from_list(args.opts)
+    rank, world, local_rank = init_distributed()
+    if cfg.MODEL.DEVICE == "cuda" and world > 1:
+        cfg.MODEL.DEVICE = "cuda:%d" % local_rank
+    cfg.OUTPUT.DIR = args.output_dir if args.output_dir.endswith("/") else args.output_dir + "/"
+    cfg.freeze()
+    os.makedirs(cfg.OUTPUT.DIR, exist_ok=True)
+    logger = setup_logger("style-transfer", cfg.OUTPUT.DIR if rank == 0 else False, rank)
+    logger.info(args)
+
+    model, device = get_model(cfg)
+    style_image = Image.open(args.style_img or cfg.DATA.STYLE_IMG_PATH).convert('RGB')      # one shared style, main.py:184-185
+    frames = sorted(glob.glob(os.path.join(args.content_dir, "*.png"))) if args.content_dir else [cfg.DATA.CONTENT_IMG_PATH]
+    if args.max_frames > 0:
+        frames = frames[: args.max_frames]
+    mine = shard_indices(len(frames), rank, world)
+    t_all = time.time()
+    results = []
+    for i in mine:
+        start = time.time()
+        content_image = Image.open(frames[i]).convert('RGB')
+        out_image = do_transfer_style(cfg, model, content_image, style_image, device)
+        if args.high_resolution:
+            out_image = do_hr_transfer_style(cfg, model, content_image, style_image, out_image, device)
+        out_image.save(os.path.join(cfg.OUTPUT.DIR, os.path.basename(frames[i])))
+        results.append(torch.from_numpy(np.asarray(out_image).copy()))
+        logger.info("frame %s: %f second per frame" % (os.path.basename(frames[i]), time.time() - start))
+    if world > 1 and results:
+        local = torch.stack(results).to(device)
+        gathered = gather_frames(local, len(frames), rank, world)
+        if rank == 0:
+            logger.info("gathered %d frames of shape %s on rank 0" % (gathered.shape[0], tuple(gathered.shape[1:])))
+    if rank == 0:
+        n = max(1, len(mine))
+        logger.info("avg time per frame on this rank: %f" % ((time.time() - t_all) / n))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,34 @@
+"""GramMSELoss with the reference's semantics (IST/model/meta_arch/gram_mse_loss.py:5-8):
+nn.MSELoss()(GramMatrix()(input), target). Forward and backward run fused in the CUDA library (Gram SYRK, (G-A)^2
+reduction, backward GEMM) when the batch is 1 as on the reference path; larger batches compose the two autograd ops."""
+import torch
+import torch.nn as nn
+
+from ... import _lib
+from .gram_matrix import GramMatrix
+
+
+class _GramMSEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target):
+        x = x.contiguous().float()
+        b, c, h, w = x.shape
+        t = target.detach().contiguous().float().view(c, c)
+        loss = torch.empty(b, device=x.device, dtype=torch.float32)
+        dx = torch.empty_like(x)
+        _lib.check(_lib.load().ist_op_gram_mse(_lib.ptr(x), _lib.ptr(t), 1.0, _lib.ptr(loss), _lib.ptr(dx), b, c, h, w,
+                                               _lib.stream_ptr()))
+        ctx.save_for_backward(dx)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return dx * g, None
+
+
+class GramMSELoss(nn.Module):
+    def forward(self, input, target):
+        if input.shape[0] == 1 and target.numel() == input.shape[1] ** 2 and not target.requires_grad:
+            return _GramMSEFn.apply(input, target)
+        return nn.MSELoss()(GramMatrix()(input), target)

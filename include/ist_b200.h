@@ -110,10 +110,12 @@ int ist_op_maxpool2x2_bwd(const float* x_dev, const float* dy_dev, float* dx_dev
 int ist_op_relu_bwd(const float* y_dev, const float* dy_dev, float* dx_dev, int batch, int C, int H, int W,
                     void* stream);
 int ist_op_gram(const float* x_dev, float* g_dev, int batch, int C, int H, int W, void* stream);
-/* weight * mean((Gram(x) - target)^2) and its gradient w.r.t. x */
+/* backward of GramMatrix for an arbitrary upstream gradient dg [batch,C,C]: dx = (dg + dg^T) F / (H*W) */
+int ist_op_gram_bwd(const float* x_dev, const float* dg_dev, float* dx_dev, int batch, int C, int H, int W, void* stream);
+/* weight * mean((Gram(x) - target)^2) [loss_dev: batch floats] and its gradient w.r.t. x; target [C,C] */
 int ist_op_gram_mse(const float* x_dev, const float* target_dev, float weight, float* loss_dev, float* dx_dev,
                     int batch, int C, int H, int W, void* stream);
-/* weight * mean((x - t)^2) and its gradient w.r.t. x */
+/* weight * mean((x - t)^2) per frame [loss_dev: batch x 2 floats, column 0 = loss] and its gradient w.r.t. x */
 int ist_op_mse(const float* x_dev, const float* t_dev, float weight, float* loss_dev, float* dx_dev, int batch,
                int C, int H, int W, void* stream);
 
