@@ -1,0 +1,335 @@
+"""bench.py — L-BFGS iterations/s of the Gatys style-transfer loop at 512x512 (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One *step* = one frame of the reference workload: targets for a fresh synthetic 512x512 radar frame + 300 closure
+evaluations (15 optimizer.step() of torch-L-BFGS semantics, IST/config/defaults.py:71, IST/model/engine/utils.py:17-45)
+through the public `optimize()` of this package. `value` = closure evaluations ("L-BFGS iters") per second over all GPUs
+with the frames resident in HBM; `e2e` = the same through host buffers (pinned H2D of the frame, D2H of the result, final
+NCCL gather when N > 1). Frames are independent problems: N GPUs process N x K frames (weak scaling), no per-step collective.
+
+`--impl reference` times the reference's own CPU path (the oracle restatement, oracle/ist_oracle.py — the reference is pure
+Python/PyTorch and its tree does not exist on the GPU box) on the host cores: each step there is a bounded sample of the
+same workload (one optimizer.step = 20 closure evaluations of a 512x512 frame).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIZE = 512
+EVALS_PER_FRAME = 300
+GF_PER_EVAL = 396.95          # algorithmic GFLOP per closure evaluation at 512^2 (SURVEY 8d / BASELINE.md 4)
+METRIC = "L-BFGS iters/sec at 512^2 per B200"
+UNIT = "closure-evals/s"
+
+
+def config_dict(n_gpus):
+    return {
+        "workload": "IST Gatys 512x512 single frame, 300 L-BFGS iters on 1xB200 (BASELINE configs[1]); one frame per step per GPU",
+        "size": SIZE, "evals_per_step": EVALS_PER_FRAME, "frames_per_step": n_gpus,
+        "weights": "synthetic Kaiming-normal VGG19 (vgg_conv.pth unavailable offline), seed 0",
+        "style_layers": "relu1_1..relu5_1", "content_layers": "relu4_2", "lbfgs": "torch defaults (lr 1, max_iter 20, history 100, no line search)",
+        "precision": "fp16 hi/lo split operands (3 MMAs) forward, bf16 hi/lo split data-gradient, fp32 accumulation promoted to registers",
+        "l2": "working set per step (~0.35 GB activations + 0.63 GB L-BFGS history) exceeds the 126 MB L2; no explicit flush",
+        "parallelism": "dp%d (independent frames, one end-of-run gather)" % n_gpus,
+    }
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))), float(d.get("hbm_gbs", 6650.0)), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        # "under load": the upper half of the samples (the sampler also sees the idle edges of the region)
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """Reference arm: the oracle's optimize() on the host CPU (all threads), bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle import ist_oracle as O
+    from oracle import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    state = O.state_to_torch(synth.vgg_state_dict(0), torch.float32)
+    style = torch.from_numpy(synth.preprocess(synth.lidar_frame(SIZE, 2)))
+    evals_per_step = 20
+    times = []
+    for i in range(args.warmup + args.steps):
+        content = torch.from_numpy(synth.preprocess(synth.radar_frame(SIZE, 1000 + i)))
+        x = content.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        _, n = O.optimize(state, content, style, x, evals_per_step, full=True)
+        dt = time.perf_counter() - t0
+        assert n == evals_per_step
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = args.steps * evals_per_step / total
+    sample = "one optimizer.step (20 closure evaluations incl. target passes) of a 512x512 frame per step, reference CPU path (oracle port), fp32"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def profile_closure(ist_b200, plan, x, reps=3):
+    """Per-launch CUDA-event timing of eager closures (same kernels as the graph replays); returns {name: [flops, bytes, ms, n]}."""
+    import ctypes
+    lib = ist_b200.load()
+    maxr = 4096
+    agg = {}
+    for _ in range(reps):
+        lib.ist_profile_begin()
+        plan.loss_and_grad(x)
+        names = ctypes.create_string_buffer(maxr * 40)
+        flops = (ctypes.c_double * maxr)()
+        nbytes = (ctypes.c_double * maxr)()
+        ms = (ctypes.c_float * maxr)()
+        n = ctypes.c_int(0)
+        ist_b200._lib.check(lib.ist_profile_end(maxr, names, flops, nbytes, ms, ctypes.byref(n)))
+        for i in range(n.value):
+            nm = names.raw[i * 40:(i + 1) * 40].split(b"\0")[0].decode()
+            a = agg.setdefault(nm, [0.0, 0.0, 0.0, 0])
+            a[0] += flops[i]; a[1] += nbytes[i]; a[2] += ms[i]; a[3] += 1
+    return agg
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ist_b200
+    from ist_b200.config import get_cfg_defaults
+    from ist_b200.main import get_model
+    from ist_b200.model.engine.utils import optimize
+    from ist_b200.parallel import gather_frames, init_distributed
+    from oracle import synth          # synthetic frames / weights only (no oracle compute on this arm)
+
+    rank, world, local_rank = init_distributed("nccl")
+    if world != args.gpus:
+        if rank == 0:
+            print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; reporting n_gpus={world}", file=sys.stderr)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = ist_b200.load()
+    ist_b200._lib.check(lib.ist_device_check())
+
+    cfg = get_cfg_defaults()
+    cfg.MODEL.DEVICE = str(dev)
+    model, _ = get_model(cfg, {k: torch.from_numpy(v) for k, v in synth.vgg_state_dict(0).items()})
+    style = torch.from_numpy(synth.preprocess(synth.lidar_frame(SIZE, 2))).to(dev)
+    n_steps = args.warmup + args.steps
+    frames_host = [torch.from_numpy(synth.preprocess(synth.radar_frame(SIZE, 1000 + rank * 1000 + i))).pin_memory() for i in range(n_steps)]
+    frames_dev = [f.to(dev) for f in frames_host]
+    result_host = torch.empty(1, 3, SIZE, SIZE).pin_memory()
+    frame_bytes = frames_host[0].numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        x = frames_dev[i].clone().requires_grad_(True)
+        optimize(model, frames_dev[i], style, x, cfg, EVALS_PER_FRAME)
+        return x
+
+    def step_e2e(i):
+        c = frames_host[i].to(dev, non_blocking=True)
+        x = c.clone().requires_grad_(True)
+        optimize(model, c, style, x, cfg, EVALS_PER_FRAME)
+        result_host.copy_(x.data, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return x
+
+    # ---- device-resident arm -------------------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = lib.ist_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    evals = 0
+    for i in range(args.warmup, n_steps):
+        step_resident(i)
+        evals += model.last_evals
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.ist_launch_count() - launches0
+    clocks = sampler.stop() if sampler is not None else None
+    t = torch.tensor([ms, float(evals), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, evals, launches = float(tmax[0]), float(tsum[1]), float(tsum[2])
+    value = evals / (ms * 1e-3)
+
+    # ---- end-to-end arm (host buffers) ------------------------------------------------------------------------------------
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e2.record()
+    evals_e = 0
+    outs = []
+    for i in range(args.warmup, n_steps):
+        outs.append(step_e2e(i).data)
+        evals_e += model.last_evals
+    if world > 1:
+        gather_frames(torch.cat(outs), world * len(outs), rank, world)
+    e3.record()
+    barrier()
+    ms_e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3 if world == 1 else 0.0)
+    te = torch.tensor([ms_e, float(evals_e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tm = te.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = te.clone()
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms_e, evals_e = float(tm[0]), float(ts[1])
+    e2e_value = evals_e / (ms_e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (rank 0, eager per-launch events) ------------------------------------------------
+    plan = model.vgg_model.plan(1, SIZE, SIZE, "relu5_1")
+    xprof = frames_dev[0] + 20.0 * torch.randn_like(frames_dev[0])
+    agg = profile_closure(ist_b200, plan, xprof)
+    groups = {}
+    for nm, (fl, by, tms, n) in agg.items():
+        key = "conv_igemm_kernel" if nm.startswith("conv_igemm") else nm
+        g = groups.setdefault(key, [0.0, 0.0, 0.0, 0])
+        g[0] += fl; g[1] += by; g[2] += tms; g[3] += n
+    total_ms = sum(g[2] for g in groups.values())
+    dom = max(groups.items(), key=lambda kv: kv[1][2])
+    peak_tf, peak_hbm, peak_src = peaks()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom[0])
+        except Exception:
+            traffic = None
+    fl, by, tms, n = dom[1]
+    if fl > 0:
+        achieved = fl / (tms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom[0], "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src + " bf16 sustained",
+                "launches_per_eval": n // 3, "share_of_closure": tms / total_ms,
+                "note": "algorithmic FLOPs (2*M*N*K, single pass) of all conv_igemm launches of one closure / their summed CUDA-event time; "
+                        "the kernel issues 3 MMAs per product (hi/lo split), so tensor-pipe activity is ~3x this fraction"}
+    else:
+        achieved = by / (tms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak_hbm, "unit": "GB/s", "frac": achieved / peak_hbm,
+                "traffic": traffic, "peak_source": peak_src, "share_of_closure": tms / total_ms}
+    kernel_table = {k: {"ms_per_eval": v[2] / 3, "launches_per_eval": v[3] // 3} for k, v in sorted(groups.items(), key=lambda kv: -kv[1][2])}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample ------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import ist_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        state = O.state_to_torch(synth.vgg_state_dict(0), torch.float32)
+        c = frames_host[0].clone()
+        s = style.cpu()
+        x = c.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        _, nev = O.optimize(state, c, s, x, 20, full=True)
+        dt = time.perf_counter() - t0
+        cpu = {"value": nev / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "one optimizer.step (20 closure evaluations + 2 target passes) of one 512x512 frame, oracle port of the reference, fp32"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16x2-split/f32-acc",
+        "data": "synthetic", "config": config_dict(world), "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": frame_bytes * world, "d2h_bytes_per_step": frame_bytes * world},
+        "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+        "frames_per_s": value / EVALS_PER_FRAME, "algorithmic_tflops": value * GF_PER_EVAL / 1e3, "kernels": kernel_table,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

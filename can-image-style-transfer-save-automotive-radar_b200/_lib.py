@@ -65,6 +65,9 @@ SIGNATURES = {
     "ist_last_error": (ctypes.c_char_p, []),
     "ist_version": (ctypes.c_int, []),
     "ist_device_check": (ctypes.c_int, []),
+    "ist_launch_count": (ctypes.c_ulonglong, []),
+    "ist_profile_begin": (ctypes.c_int, []),
+    "ist_profile_end": (ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), _c_float_p, _c_int_p]),
     "ist_plan_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.POINTER(LayerDesc), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "ist_plan_destroy": (ctypes.c_int, [_vp]),
     "ist_plan_set_weights": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp]),

@@ -464,7 +464,7 @@ content_partial_kernel(const uint16_t* __restrict__ f_hi, const uint16_t* __rest
 //   target mode: g_out <- G.   loss mode: diff <- G - A; per-block sum(diff^2) and max|diff|.
 // ------------------------------------------------------------------------------------------------------------
 struct GramLayer {
-    const float* partial;   // [NB][splits][C][C], only tiles with col_tile >= row_tile written
+    const float* partial;   // [NB][splits][C][C] (the SYRK kernel also stores the mirrored tiles)
     const float* target;    // [C][C] shared by all frames (loss mode)
     float* g_out;           // [NB][C][C] (target mode) or nullptr
     float* diff;            // [NB][C][C]
@@ -479,7 +479,7 @@ struct GramLayer {
     float weight;           // loss weight (STYLE_WEIGHTS[k], defaults.py:68)
     float bwd_coef;         // 2*w / (C^2 * H*W * s_act)
 };
-constexpr int GRAM_FIN_BLOCKS = 32;
+constexpr int GRAM_FIN_BLOCKS = 64;
 struct GramFinalizeParams {
     GramLayer L[8];
     int n_layers, NB, loss_stride;
@@ -493,10 +493,8 @@ gram_reduce_kernel(const GramFinalizeParams p) {
     const size_t CC = (size_t)C * C;
     float s = 0.f, mx = 0.f;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < CC; e += (size_t)gridDim.x * blockDim.x) {
-        const int c1 = (int)(e / C), c2 = (int)(e % C);
-        const size_t src = ((c1 >> 7) <= (c2 >> 7)) ? e : ((size_t)c2 * C + c1);
         float g = 0.f;
-        for (int sp = 0; sp < L.splits; ++sp) g += L.partial[((size_t)fr * L.splits + sp) * CC + src];
+        for (int sp = 0; sp < L.splits; ++sp) g += L.partial[((size_t)fr * L.splits + sp) * CC + e];
         g *= L.g_scale;
         if (L.g_out != nullptr) {
             L.g_out[(size_t)fr * CC + e] = g;

@@ -5,7 +5,7 @@
 // index is the pixel, so both operands are *MN-major* for the tensor core (channel contiguous): a TMA box
 // of [64 pixels][64 channels] with 128-byte swizzle is exactly one column of MN-major SW128 atoms
 // (8 pixel rows of 128 B each), SBO = 1024 between 8-pixel groups, LBO = 8192 between 64-channel groups.
-// Only tiles with n_tile >= m_tile are computed (SYRK); gram_finalize mirrors them. Diagonal tiles reuse
+// Only tiles with n_tile >= m_tile are computed (SYRK); off-diagonal tiles are also stored mirrored. Diagonal tiles reuse
 // the A tile as B (no second load). Split over pixels gives >= 1 CTA per SM even for C = 64; partial
 // results go to a [split] array that gram_finalize sums in a fixed order (deterministic, no atomics).
 // 3-pass split (hi*hi + hi*lo + lo*hi) and the short-chain / register-promotion accumulation scheme of
@@ -214,6 +214,13 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
                     for (int q = 0; q < 8; ++q)
                         d[q] = make_float4(acc[c0 + 4 * q], acc[c0 + 4 * q + 1], acc[c0 + 4 * q + 2], acc[c0 + 4 * q + 3]);
                 }
+            }
+            if (!diag) {
+                // mirrored tile G[c2][c1] = G[c1][c2]: for a fixed column j the 32 lanes of a warp hold 32 consecutive c1,
+                // so these scalar stores coalesce; gram_reduce then reads every element at its own (coalesced) address.
+                float* mir = p.partial + (((size_t)fr * p.splits + split) * p.C + (size_t)nt * 128) * (size_t)p.C + c1;
+#pragma unroll
+                for (int j = 0; j < 128; ++j) mir[(size_t)j * p.C] = acc[j];
             }
         }
     }

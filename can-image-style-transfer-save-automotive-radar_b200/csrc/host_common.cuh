@@ -43,6 +43,45 @@ inline int fail(int code, const char* fmt, ...) {
         if (rc__ != IST_OK) return rc__; \
     } while (0)
 
+// ----------------------------------------------------------------------------------------------------------
+// launch bookkeeping: a process-wide count of kernels this library launched (graph replays count their nodes) and an
+// optional per-launch profiler (CUDA events around every launch, eager mode only) used by bench.py for the roofline.
+// ----------------------------------------------------------------------------------------------------------
+struct ProfRec {
+    char name[40];
+    double flops, bytes;      // algorithmic work of the launch
+    cudaEvent_t e0, e1;
+};
+struct LaunchBook {
+    unsigned long long launches = 0;   // kernels launched or replayed
+    unsigned long long captured = 0;   // kernels recorded into the graph being captured
+    bool capturing = false;
+    bool profiling = false;
+    std::vector<ProfRec> recs;
+};
+inline LaunchBook& book() {
+    static LaunchBook b;
+    return b;
+}
+inline void launch_pre(const char* name, double flops, double bytes, cudaStream_t st) {
+    LaunchBook& b = book();
+    if (b.capturing) b.captured++; else b.launches++;
+    if (b.profiling && !b.capturing) {
+        ProfRec r;
+        memset(&r, 0, sizeof(r));
+        strncpy(r.name, name, sizeof(r.name) - 1);
+        r.flops = flops; r.bytes = bytes;
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, st);
+        b.recs.push_back(r);
+    }
+}
+inline void launch_post(cudaStream_t st) {
+    LaunchBook& b = book();
+    if (b.profiling && !b.capturing && !b.recs.empty()) cudaEventRecord(b.recs.back().e1, st);
+}
+
 inline int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -126,7 +165,13 @@ inline int launch_conv_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
     }
     const int total = p.NB * p.tiles_x * p.tiles_y * p.tiles_n;
     const int grid = total < num_sms() ? total : num_sms();
+    const double px = (double)p.NB * p.H * p.W;
+    const int planes = p.passes == 3 ? 2 : 1;
+    launch_pre(p.taps == 9 ? (p.mode == CONV_FWD ? "conv_igemm_fwd" : "conv_igemm_dgrad") : "conv_igemm_gram_bwd",
+               2.0 * px * p.Cout * p.Cin * p.taps,
+               planes * 2.0 * (px * p.Cin + (double)p.taps * p.Cin * p.Cout) + px * p.Cout * (p.out_f32 != nullptr ? 4.0 : 4.0), st);
     conv_igemm_kernel<N_TILE><<<grid, 192, ConvCfg<N_TILE>::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    launch_post(st);
     IST_CUDA(cudaGetLastError());
     return IST_OK;
 }
@@ -158,7 +203,7 @@ inline void gram_split_plan(int NB, int HW, int C, int* splits, int* chunks_per_
     const int tiles_c = (C + 127) / 128;
     const int tri = tiles_c * (tiles_c + 1) / 2;
     const int total_chunks = (HW + 63) / 64;
-    int want = (2 * num_sms() + tri * NB - 1) / (tri * NB);
+    int want = (num_sms() + tri * NB - 1) / (tri * NB);     // ~one CTA per SM; accuracy does not depend on the split (register promotion)
     if (want < 1) want = 1;
     if (want > total_chunks) want = total_chunks;
     if (want > 64) want = 64;
@@ -186,7 +231,9 @@ inline int launch_gram(cudaStream_t st, const CUtensorMap& m_hi, const CUtensorM
     p.partial = partial;
     const int tri = p.tiles_c * (p.tiles_c + 1) / 2;
     dim3 grid(splits, tri, NB);
+    launch_pre("gram_syrk", 2.0 * NB * (double)HW * C * C, 4.0 * NB * (double)HW * C + 4.0 * NB * splits * (double)C * C, st);
     gram_syrk_kernel<<<grid, 192, GramCfg::SMEM_BYTES, st>>>(m_hi, m_lo, p);
+    launch_post(st);
     IST_CUDA(cudaGetLastError());
     return IST_OK;
 }
@@ -198,6 +245,15 @@ inline int ew_grid(size_t work_items, int block) {
     if (g < 1) g = 1;
     return (int)g;
 }
+
+// launch an elementwise / reduction kernel with bookkeeping: IST_EW("name", bytes, stream, kernel<<<...>>>(...));
+#define IST_EW(name, bytes, st, ...)                 \
+    do {                                             \
+        ::ist::launch_pre(name, 0.0, (double)(bytes), st); \
+        __VA_ARGS__;                                 \
+        ::ist::launch_post(st);                      \
+        IST_CUDA(cudaGetLastError());                \
+    } while (0)
 
 struct DevMem {
     std::vector<void*> ptrs;

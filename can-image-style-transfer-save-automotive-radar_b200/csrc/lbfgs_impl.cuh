@@ -463,6 +463,7 @@ struct ist_lbfgs {
     cudaGraphExec_t graph_exec = nullptr;
     float* graph_x = nullptr;
     bool use_graph = true;
+    unsigned long long graph_kernels = 0;
     std::vector<ist::LbFrame> host_frames;
 };
 
@@ -474,14 +475,11 @@ inline int lbfgs_enqueue_step(ist_lbfgs* O, float* x, cudaStream_t st) {
     for (int it = 1; it <= P.max_iter; ++it) {
         IST_TRY(ist_plan_loss_and_grad(O->plan, x, O->g, O->losses, (void*)st));
         P.it = it;
-        lbfgs_prep_kernel<<<(P.NB + 63) / 64, 64, 0, st>>>(P);
-        IST_CUDA(cudaGetLastError());
-        lbfgs_dots_kernel<<<dim3(P.nblk, P.NB), 256, 0, st>>>(P);
-        IST_CUDA(cudaGetLastError());
-        lbfgs_solve_kernel<<<P.NB, 128, lb_solve_smem(P.m), st>>>(P);
-        IST_CUDA(cudaGetLastError());
-        lbfgs_update_kernel<<<dim3(P.nblk, P.NB), 256, 0, st>>>(P);
-        IST_CUDA(cudaGetLastError());
+        const double vb = 4.0 * P.NB * (double)P.n;
+        IST_EW("lbfgs_prep", 64.0, st, lbfgs_prep_kernel<<<(P.NB + 63) / 64, 64, 0, st>>>(P));
+        IST_EW("lbfgs_dots", vb * (3 + 2.0 * P.m), st, lbfgs_dots_kernel<<<dim3(P.nblk, P.NB), 256, 0, st>>>(P));
+        IST_EW("lbfgs_solve", 16.0 * P.m * P.m, st, lbfgs_solve_kernel<<<P.NB, 128, lb_solve_smem(P.m), st>>>(P));
+        IST_EW("lbfgs_update", vb * (9 + 2.0 * P.m), st, lbfgs_update_kernel<<<dim3(P.nblk, P.NB), 256, 0, st>>>(P));
     }
     return IST_OK;
 }
@@ -565,7 +563,11 @@ int ist_lbfgs_step(ist_lbfgs* O, float* x_dev, int* evals_out, float* loss_out, 
             if (O->cap_stream == nullptr) IST_CUDA(cudaStreamCreateWithFlags(&O->cap_stream, cudaStreamNonBlocking));
             IST_CUDA(cudaStreamSynchronize(st));
             IST_CUDA(cudaStreamBeginCapture(O->cap_stream, cudaStreamCaptureModeThreadLocal));
+            book().capturing = true;
+            book().captured = 0;
             int rc = lbfgs_enqueue_step(O, x_dev, O->cap_stream);
+            book().capturing = false;
+            O->graph_kernels = book().captured;
             cudaGraph_t graph = nullptr;
             cudaError_t e = cudaStreamEndCapture(O->cap_stream, &graph);
             if (rc != IST_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -576,6 +578,7 @@ int ist_lbfgs_step(ist_lbfgs* O, float* x_dev, int* evals_out, float* loss_out, 
             O->graph_x = x_dev;
         }
         IST_CUDA(cudaGraphLaunch(O->graph_exec, st));
+        book().launches += O->graph_kernels;
     } else {
         IST_TRY(lbfgs_enqueue_step(O, x_dev, st));
     }

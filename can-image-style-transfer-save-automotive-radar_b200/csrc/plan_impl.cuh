@@ -98,8 +98,10 @@ int run_forward(ist_plan* P, const float* x, int upto, cudaStream_t st) {
             if (!L.has_weights) return fail(IST_ERR_STATE, "conv layer %d has no weights (ist_plan_set_weights)", l);
             if (l == 0) {
                 const size_t px = (size_t)P->NB * L.H * L.W;
+                launch_pre("conv_first_fwd", 2.0 * px * 64 * 27, px * (12.0 + 256.0), st);
                 conv_first_fwd_kernel<64><<<(unsigned)((px + 127) / 128), 128, 0, st>>>(x, L.w_f32, L.bias, L.out.hi, L.out.lo,
                                                                                      P->NB, L.H, L.W, kActScale);
+                launch_post(st);
                 IST_CUDA(cudaGetLastError());
             } else {
                 ConvParams p;
@@ -116,8 +118,8 @@ int run_forward(ist_plan* P, const float* x, int upto, cudaStream_t st) {
         } else {
             const Layer& I = P->layers[l - 1];
             const size_t items = (size_t)P->NB * L.H * L.W * (L.C / 8);
-            maxpool_fwd_kernel<<<ew_grid(items, 256), 256, 0, st>>>(I.out.hi, I.out.lo, L.out.hi, L.out.lo, P->NB, I.H, I.W, I.C);
-            IST_CUDA(cudaGetLastError());
+            IST_EW("maxpool_fwd", 5.0 * L.out_elems * 4, st,
+                   maxpool_fwd_kernel<<<ew_grid(items, 256), 256, 0, st>>>(I.out.hi, I.out.lo, L.out.hi, L.out.lo, P->NB, I.H, I.W, I.C));
         }
     }
     P->forwarded_upto = upto;
@@ -224,8 +226,8 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         r.out_hi = L.dY.hi; r.out_lo = L.dY.lo;
         r.out_f32 = to_f32 ? f32_out : nullptr;
         const size_t items = (size_t)NB * ((L.H + 1) / 2) * ((L.W + 1) / 2) * (L.C / 8);
-        grad_route_kernel<<<ew_grid(items, 256), 256, 0, st>>>(r);
-        IST_CUDA(cudaGetLastError());
+        IST_EW("grad_route", (double)L.out_elems * (4 + 4 + (g_pool != nullptr ? 1 : 0) + (addend != nullptr ? 4 : 0) + (content ? 8 : 0)), st,
+               grad_route_kernel<<<ew_grid(items, 256), 256, 0, st>>>(r));
         return IST_OK;
     };
 
@@ -283,7 +285,9 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
     }
     Layer& L0 = P->layers[0];
     const size_t px = (size_t)NB * L0.H * L0.W;
+    launch_pre("conv_first_dgrad", 2.0 * px * 64 * 27, px * (12.0 + 256.0), st);
     conv_first_dgrad_kernel<64><<<(unsigned)((px + 127) / 128), 128, 0, st>>>(L0.dY.hi, L0.dY.lo, L0.w_f32, grad, NB, L0.H, L0.W);
+    launch_post(st);
     IST_CUDA(cudaGetLastError());
     return IST_OK;
 }
@@ -302,10 +306,13 @@ int run_losses(ist_plan* P, float* losses_dev, cudaStream_t st) {
     }
     if (gp.n_layers > 0) {
         dim3 grid(GRAM_FIN_BLOCKS, gp.n_layers, P->NB);
-        gram_reduce_kernel<<<grid, 256, 0, st>>>(gp);
-        IST_CUDA(cudaGetLastError());
-        gram_dmat_kernel<<<grid, 256, 0, st>>>(gp);
-        IST_CUDA(cudaGetLastError());
+        double rb = 0, db = 0;
+        for (int k = 0; k < gp.n_layers; ++k) {
+            rb += (double)P->NB * gp.L[k].C * gp.L[k].C * 4.0 * (gp.L[k].splits + 2);
+            db += (double)P->NB * gp.L[k].C * gp.L[k].C * 12.0;
+        }
+        IST_EW("gram_reduce", rb, st, gram_reduce_kernel<<<grid, 256, 0, st>>>(gp));
+        IST_EW("gram_dmat", db, st, gram_dmat_kernel<<<grid, 256, 0, st>>>(gp));
     }
     LossTotalParams lt;
     memset(&lt, 0, sizeof(lt));
@@ -319,15 +326,14 @@ int run_losses(ist_plan* P, float* losses_dev, cudaStream_t st) {
         if (!L.content_set) return fail(IST_ERR_STATE, "content target %d not captured", k);
         const size_t n8 = (size_t)L.H * L.W * L.C / 8;
         dim3 grid(kContentBlocks, P->NB);
-        content_partial_kernel<<<grid, 256, 0, st>>>(L.out.hi, L.out.lo, L.T.hi, L.T.lo, n8, L.c_partial);
-        IST_CUDA(cudaGetLastError());
+        IST_EW("content_partial", (double)L.out_elems * 8, st,
+               content_partial_kernel<<<grid, 256, 0, st>>>(L.out.hi, L.out.lo, L.T.hi, L.T.lo, n8, L.c_partial));
         lt.c_partial[k] = L.c_partial;
         lt.c_slot[k] = P->n_style + k;
         lt.c_scale[k] = (float)((double)L.content_w / ((double)L.C * L.H * L.W * kActScale * kActScale));
         lt.n_content++;
     }
-    loss_total_kernel<<<(P->NB + 63) / 64, 64, 0, st>>>(lt);
-    IST_CUDA(cudaGetLastError());
+    IST_EW("loss_total", 64.0 * P->NB, st, loss_total_kernel<<<(P->NB + 63) / 64, 64, 0, st>>>(lt));
     return IST_OK;
 }
 
@@ -348,6 +354,39 @@ extern "C" {
 const char* ist_last_error(void) { return last_error().c_str(); }
 int ist_version(void) { return 1; }
 int ist_device_check(void) { return check_device(); }
+
+unsigned long long ist_launch_count(void) { return book().launches; }
+
+int ist_profile_begin(void) {
+    LaunchBook& b = book();
+    for (ProfRec& r : b.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    b.recs.clear();
+    b.profiling = true;
+    return IST_OK;
+}
+
+int ist_profile_end(int max_records, char* names, double* flops, double* bytes, float* ms, int* n_out) {
+    LaunchBook& b = book();
+    b.profiling = false;
+    IST_CUDA(cudaDeviceSynchronize());
+    int n = 0;
+    for (ProfRec& r : b.recs) {
+        if (n < max_records) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, r.e0, r.e1);
+            if (names != nullptr) memcpy(names + (size_t)n * 40, r.name, 40);
+            if (flops != nullptr) flops[n] = r.flops;
+            if (bytes != nullptr) bytes[n] = r.bytes;
+            if (ms != nullptr) ms[n] = t;
+            ++n;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    b.recs.clear();
+    if (n_out != nullptr) *n_out = n;
+    return IST_OK;
+}
 
 int ist_plan_create(ist_plan** out, int n_layers, const ist_layer_desc* layers, int batch, int H, int W) {
     if (out == nullptr || layers == nullptr || n_layers < 1 || batch < 1 || H < 1 || W < 1)

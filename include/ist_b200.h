@@ -48,6 +48,14 @@ int ist_version(void);
 /* 0 when the current CUDA device can run the kernels (compute capability 10.x), IST_ERR_DEVICE otherwise. */
 int ist_device_check(void);
 
+/* kernels launched by this library in this process so far (kernels inside a replayed CUDA graph are counted per replay) */
+unsigned long long ist_launch_count(void);
+/* per-launch profiling for benchmarks: between begin and end every kernel launched eagerly (not through a graph) is
+ * bracketed by CUDA events on its stream. end() synchronises the device and returns up to max_records records:
+ * names [n][40] chars, algorithmic flops / bytes per launch, elapsed milliseconds. */
+int ist_profile_begin(void);
+int ist_profile_end(int max_records, char* names, double* flops, double* bytes, float* ms, int* n_out);
+
 /* plan: VGG.__init__ (IST/model/meta_arch/vgg.py:6-42) for one (batch, H, W) ------------------------------ */
 /* layers[] follows cfg.MODEL.VGG.FORWARD_SEQ (IST/config/defaults.py:48-54) truncated at the deepest layer the
  * caller will ever request. The first layer must be a conv with cin == 3; all other convs need cin, cout % 64 == 0. */

@@ -102,7 +102,7 @@ def loss_and_grad(state, x, targets, **kw):
     ll = layer_losses(state, xg, targets, **kw)
     loss = sum(ll)
     loss.backward()
-    return [float(l) for l in ll], float(loss), xg.grad.detach()
+    return [float(l.detach()) for l in ll], float(loss.detach()), xg.grad.detach()
 
 
 def optimize(state, content_image, style_image, optimized_image, max_iterations, full=True, trace=None, **kw):

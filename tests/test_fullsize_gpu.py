@@ -1,0 +1,54 @@
+"""BASELINE.json's full size (512x512, config 2) checked through size-independent properties: exact zero content loss at
+x0, bitwise determinism, consistency of the analytic image gradient with a central finite difference of the loss along a
+random direction, and sanity of one optimizer.step."""
+import pytest
+import torch
+
+from ist_b200.model.engine.utils import optimize
+from gpu_common import build_model, frames, noise_like, prepare_plan, strict_fp32
+
+pytestmark = pytest.mark.gpu
+dev = torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def setup():
+    strict_fp32()
+    cfg, model = build_model(dev)
+    content, style = frames(512, dev, "smooth")
+    plan = prepare_plan(model, cfg, content, style)
+    return cfg, model, content, style, plan
+
+
+def test_content_loss_zero_and_determinism(setup):
+    cfg, model, content, style, plan = setup
+    l0, g0 = plan.loss_and_grad(content)
+    l0, g0 = l0.clone(), g0.clone()
+    assert float(l0[0, 5]) == 0.0 and torch.isfinite(g0).all() and torch.isfinite(l0).all()
+    l1, g1 = plan.loss_and_grad(content)
+    assert torch.equal(l0, l1) and torch.equal(g0, g1)
+
+
+def test_gradient_matches_finite_difference(setup):
+    cfg, model, content, style, plan = setup
+    x = content + noise_like(content)
+    _, g = plan.loss_and_grad(x)
+    g = g.clone()
+    d = noise_like(content, seed=11, scale=1.0)
+    d = d / d.norm()
+    eps = 2.0        # the loss is piecewise smooth; a step of 2 intensity levels along a unit direction keeps fp32 loss noise small
+    lp = plan.loss_and_grad(x + eps * d)[0][0, 6].double().item()
+    lm = plan.loss_and_grad(x - eps * d)[0][0, 6].double().item()
+    fd = (lp - lm) / (2 * eps)
+    an = float((g.double() * d.double()).sum())
+    print(f"directional derivative analytic {an:.6e} finite-difference {fd:.6e}")
+    assert abs(fd - an) <= 2e-2 * abs(an)
+
+
+def test_one_optimizer_step_at_full_size(setup):
+    cfg, model, content, style, plan = setup
+    l_start = plan.loss_and_grad(content)[0][0, 6].item()
+    x = content.clone().requires_grad_(True)
+    optimize(model, content, style, x, cfg, 20)
+    assert model.last_evals == 20
+    assert model.last_losses[0, 6].item() < 0.5 * l_start
