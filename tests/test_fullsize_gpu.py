@@ -34,9 +34,13 @@ def test_gradient_matches_finite_difference(setup):
     x = content + noise_like(content)
     _, g = plan.loss_and_grad(x)
     g = g.clone()
-    d = noise_like(content, seed=11, scale=1.0)
+    # direction: the normalised gradient plus a random unit vector. The total loss is ~1e8 in fp32 (one ulp = 8), so the
+    # finite difference needs a direction with a large derivative (||g||); a purely random unit direction changes the loss
+    # by less than one ulp. eps = 16 along a unit direction moves each pixel by ~0.02 levels (linear regime).
+    r = noise_like(content, seed=11, scale=1.0)
+    d = g / g.norm() + r / r.norm()
     d = d / d.norm()
-    eps = 2.0        # the loss is piecewise smooth; a step of 2 intensity levels along a unit direction keeps fp32 loss noise small
+    eps = 16.0
     lp = plan.loss_and_grad(x + eps * d)[0][0, 6].double().item()
     lm = plan.loss_and_grad(x - eps * d)[0][0, 6].double().item()
     fd = (lp - lm) / (2 * eps)
@@ -50,5 +54,8 @@ def test_one_optimizer_step_at_full_size(setup):
     l_start = plan.loss_and_grad(content)[0][0, 6].item()
     x = content.clone().requires_grad_(True)
     optimize(model, content, style, x, cfg, 20)
-    assert model.last_evals == 20
+    # the first step of torch's L-BFGS is t = 1/||g||_1 (lbfgs.py:455): at 512^2 it moves most pixels by less than one fp32
+    # ulp, so the `abs(loss - prev_loss) < tolerance_change` exit (lbfgs.py:521) may legitimately fire after 2 evaluations,
+    # in which case optimize() runs a second step() of 20 (reference loop, utils.py:28,43)
+    assert 20 <= model.last_evals < 40
     assert model.last_losses[0, 6].item() < 0.5 * l_start
