@@ -27,12 +27,14 @@ struct HaloCfg {
     static constexpr int EXACT_BYTES = TW * TH * 128;              // 16384
     static constexpr int A_PLANE = 23 * 1024;                      // 23552 >= HALO_BYTES, keeps every plane 1024-aligned
     static constexpr int A_STAGE = 2 * A_PLANE;
-    static constexpr int A_STAGES = (N_TILE == 128) ? 2 : 3;
+    static constexpr int A_STAGES = 2;
     static constexpr int B_PLANE = N_TILE * 128;
     static constexpr int B_STAGE = 2 * B_PLANE;
-    static constexpr int B_STAGES = 4;
+    static constexpr int B_STAGES = (N_TILE == 128) ? 3 : 4;
     static constexpr int TMEM_COLS = (4 * N_TILE < 32) ? 32 : 4 * N_TILE;
-    static constexpr int SMEM_BYTES = A_STAGES * A_STAGE + B_STAGES * B_STAGE + 256 + 1024;
+    static constexpr int OUT_PLANE = 128 * 128;                    // output staging: 128 pixels x 64 channels x 2 B per plane
+    static constexpr int OUT_BYTES = 2 * OUT_PLANE;                // hi + lo
+    static constexpr int SMEM_BYTES = A_STAGES * A_STAGE + B_STAGES * B_STAGE + OUT_BYTES + 256 + 1024;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_bo(uint32_t smem_addr, uint32_t sbo, uint32_t use_base_offset) {
@@ -41,17 +43,33 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_bo(uint32_t smem_addr, uint3
     return d;
 }
 
+// Forward epilogue on registers for 32 consecutive channels starting at channel cb: relu(v + bias) * out_scale split into
+// fp16 hi / lo packs (same arithmetic as the CONV_FWD branch of conv_epilogue_32).
+__device__ __forceinline__ void conv_epilogue_regs_32(const ConvParams& p, const float (&v)[32], int cb, uint32_t (&hi)[16],
+                                                      uint32_t (&lo)[16]) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        const float a = fmaxf(v[j] + __ldg(p.bias + cb + j), 0.f) * p.out_scale;
+        const float b = fmaxf(v[j + 1] + __ldg(p.bias + cb + j + 1), 0.f) * p.out_scale;
+        const uint32_t h = pack_h2(a, b);
+        hi[j >> 1] = h;
+        lo[j >> 1] = pack_h2(a - h_lo_f(h), b - h_hi_f(h));
+    }
+}
+
 template <int N_TILE>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(224, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                 const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
                  const ConvParams p) {
     using Cfg = HaloCfg<N_TILE>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = smem_base;
     const uint32_t b_base = smem_base + Cfg::A_STAGES * Cfg::A_STAGE;
-    const uint32_t bar_base = b_base + Cfg::B_STAGES * Cfg::B_STAGE;
+    const uint32_t o_base = b_base + Cfg::B_STAGES * Cfg::B_STAGE;      // output staging (1024-aligned planes)
+    const uint32_t bar_base = o_base + Cfg::OUT_BYTES;
     // barriers (8 B each): a_full[3] @0, a_empty[3] @24, b_full[4] @48, b_empty[4] @80, main_full[2] @112,
     // main_empty[2] @128, cross_full[2] @144, cross_empty[2] @160, tmem base address @192
     auto afull = [&](int s) { return bar_base + 8u * s; };
@@ -68,6 +86,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    long long* dbg = p.dbg_times != nullptr ? p.dbg_times + 8 * (size_t)blockIdx.x : nullptr;
+    if (dbg != nullptr && threadIdx.x == 0) dbg[0] = clock64();
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA_hi);
@@ -76,8 +96,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             tma_prefetch_desc(&tmA_lo);
             tma_prefetch_desc(&tmB_lo);
         }
-        for (int s = 0; s < Cfg::A_STAGES; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
-        for (int s = 0; s < Cfg::B_STAGES; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+        // a stage is released by the commits of both issuing warps (main chain + cross terms) when the operands are split
+        const uint32_t releasers = (p.passes == 3) ? 2u : 1u;
+        for (int s = 0; s < Cfg::A_STAGES; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), releasers); }
+        for (int s = 0; s < Cfg::B_STAGES; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), releasers); }
         for (uint32_t a = 0; a < 2; ++a) {
             mbar_init(mfull(a), 1);
             mbar_init(mempty(a), 128);
@@ -91,6 +113,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    if (dbg != nullptr && threadIdx.x == 0) dbg[1] = clock64();
 
     const int tiles_m = p.NB * p.tiles_y * p.tiles_x;
     const int total_tiles = tiles_m * p.tiles_n;
@@ -104,7 +127,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t a_tx = (uint32_t)(planes * (halo ? Cfg::HALO_BYTES : Cfg::EXACT_BYTES));
     const uint32_t b_tx = (uint32_t)(planes * Cfg::B_PLANE);
     const uint32_t a_sbo = halo ? (uint32_t)(Cfg::PW * 128) : 1024u;
-    const uint32_t use_bo = (uint32_t)p.desc_base_offset;
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer ------------------------------------------------
@@ -121,86 +143,120 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 for (int cc = 0; cc < cchunks; ++cc) {
                     mbar_wait(aempty(as), aph ^ 1u);
                     const uint32_t sA = a_base + as * Cfg::A_STAGE;
+                    if (p.dbg_flags & 2) { mbar_arrive(afull(as)); } else {
                     mbar_arrive_expect_tx(afull(as), a_tx);
                     tma_load_4d(sA, &tmA_hi, afull(as), cc * 64, x0, y0, fr);
                     if (split) tma_load_4d(sA + Cfg::A_PLANE, &tmA_lo, afull(as), cc * 64, x0, y0, fr);
+                    }
                     if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
                     for (int tap = 0; tap < taps; ++tap) {
                         const int bz = p.b_frame ? fr : tap;
                         mbar_wait(bempty(bs), bph ^ 1u);
                         const uint32_t sB = b_base + bs * Cfg::B_STAGE;
+                        if (p.dbg_flags & 4) { mbar_arrive(bfull(bs)); } else {
                         mbar_arrive_expect_tx(bfull(bs), b_tx);
                         tma_load_3d(sB, &tmB_hi, bfull(bs), cc * 64, n0, bz);
                         if (split) tma_load_3d(sB + Cfg::B_PLANE, &tmB_lo, bfull(bs), cc * 64, n0, bz);
+                        }
                         if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer --------------------------------------------------
+        // ------------------------------------------ MMA issuer 1: hi*hi chains ------------------------------------------
+        // Two warps issue MMAs (this one the short hi*hi chains, warp 6 the hi*lo + lo*hi cross terms): a single issuing
+        // thread sustains about one tcgen05.mma per ~100 cycles (measured), below the 64-cycle execution time of a
+        // 128x128x16 MMA, and the two streams write different accumulators, so they are independent.
+        // The whole warp walks the (warp-uniform) loop; one elected lane issues. Descriptors are a constant high word plus
+        // a low word (start address >> 4) that only receives small adds.
+        const uint32_t a_hi_w = ((a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+        const uint32_t b_hi_w = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t idesc = p.idesc;
+        const int kyn = halo ? 3 : 1;
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
         uint32_t mcount = 0, tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-            const uint32_t xa = tcount & 1u;
-            const uint32_t d_cross = tmem_base + (uint32_t)(2 * N_TILE) + xa * N_TILE;
-            if (split) {
-                mbar_wait(xempty(xa), ((tcount >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-            }
             int kit = 0;
             for (int cc = 0; cc < cchunks; ++cc) {
                 mbar_wait(afull(as), aph);
-                const uint32_t sA = a_base + as * Cfg::A_STAGE;
-                for (int tap = 0; tap < taps; ++tap, ++kit) {
-                    const int in_chain = kit % promote;
-                    const uint32_t mb = mcount & 1u;
-                    if (in_chain == 0) {
-                        mbar_wait(mempty(mb), ((mcount >> 1) & 1u) ^ 1u);
-                    }
-                    mbar_wait(bfull(bs), bph);
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t d_main = tmem_base + mb * N_TILE;
-                        const uint32_t sB = b_base + bs * Cfg::B_STAGE;
-                        uint32_t a_off = 0;
-                        if (halo) a_off = (uint32_t)(((tap / 3) * Cfg::PW + (tap % 3)) * 128);
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            const uint64_t a_hi = umma_desc_sw128_bo(sA + a_off + k4 * 32, a_sbo, use_bo);
-                            const uint64_t b_hi = umma_smem_desc_sw128(sB + k4 * 32, 0, 1024);
-                            umma_f16(d_main, a_hi, b_hi, p.idesc, (in_chain | k4) != 0 ? 1u : 0u);
-                        }
+                const uint32_t a_lo_stage = (a_base + as * Cfg::A_STAGE) >> 4;
+                for (int ky = 0; ky < kyn; ++ky) {
+                    for (int kx = 0; kx < kyn; ++kx, ++kit) {
+                        const int in_chain = kit % promote;
+                        const uint32_t mb = mcount & 1u;
                         const bool chain_end = (in_chain == promote - 1) || (kit == kiters - 1);
-                        if (chain_end) umma_commit(mfull(mb));
-                        if (split) {
+                        if (in_chain == 0) mbar_wait(mempty(mb), ((mcount >> 1) & 1u) ^ 1u);
+                        mbar_wait(bfull(bs), bph);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            if (dbg != nullptr && tcount == 0 && kit == 0) dbg[2] = clock64();
+                            const uint32_t d_main = tmem_base + mb * N_TILE;
+                            const uint32_t a_lo = a_lo_stage + (uint32_t)((ky * Cfg::PW + kx) * 8);
+                            const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
 #pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4) {
-                                const uint64_t a_hi = umma_desc_sw128_bo(sA + a_off + k4 * 32, a_sbo, use_bo);
-                                const uint64_t a_lo = umma_desc_sw128_bo(sA + Cfg::A_PLANE + a_off + k4 * 32, a_sbo, use_bo);
-                                const uint64_t b_hi = umma_smem_desc_sw128(sB + k4 * 32, 0, 1024);
-                                const uint64_t b_lo = umma_smem_desc_sw128(sB + Cfg::B_PLANE + k4 * 32, 0, 1024);
-                                umma_f16(d_cross, a_hi, b_lo, p.idesc, (kit | k4) != 0 ? 1u : 0u);
-                                umma_f16(d_cross, a_lo, b_hi, p.idesc, 1u);
-                            }
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                umma_f16_lh(d_main, a_lo + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, (in_chain | k4) != 0 ? 1u : 0u);
+                            if (chain_end) umma_commit(mfull(mb));
+                            umma_commit(bempty(bs));
+                            if (ky == kyn - 1 && kx == kyn - 1) umma_commit(aempty(as));
+                            if (dbg != nullptr && kit == kiters - 1) dbg[3] = clock64();
                         }
-                        umma_commit(bempty(bs));
-                        if (tap == taps - 1) umma_commit(aempty(as));
-                        if (split && kit == kiters - 1) umma_commit(xfull(xa));
+                        __syncwarp();
+                        if (chain_end) ++mcount;
+                        if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                     }
-                    __syncwarp();
-                    if (in_chain == promote - 1 || kit == kiters - 1) ++mcount;
-                    if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                 }
                 if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
+            }
+        }
+    } else if (warp == 6) {
+        // ------------------------------------- MMA issuer 2: hi*lo + lo*hi cross terms -----------------------------------
+        if (split) {
+            const uint32_t a_hi_w = ((a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+            const uint32_t b_hi_w = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t idesc = p.idesc;
+            const int kyn = halo ? 3 : 1;
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0;
+            uint32_t tcount = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t xa = tcount & 1u;
+                const uint32_t d_cross = tmem_base + (uint32_t)(2 * N_TILE) + xa * N_TILE;
+                mbar_wait(xempty(xa), ((tcount >> 1) & 1u) ^ 1u);
+                int kit = 0;
+                for (int cc = 0; cc < cchunks; ++cc) {
+                    mbar_wait(afull(as), aph);
+                    const uint32_t a_lo_stage = (a_base + as * Cfg::A_STAGE) >> 4;
+                    for (int ky = 0; ky < kyn; ++ky) {
+                        for (int kx = 0; kx < kyn; ++kx, ++kit) {
+                            mbar_wait(bfull(bs), bph);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint32_t a_lo = a_lo_stage + (uint32_t)((ky * Cfg::PW + kx) * 8);
+                                const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4) {
+                                    umma_f16_lh(d_cross, a_lo + 2 * k4, a_hi_w, b_lo + (Cfg::B_PLANE >> 4) + 2 * k4, b_hi_w, idesc,
+                                                (kit | k4) != 0 ? 1u : 0u);
+                                    umma_f16_lh(d_cross, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, 1u);
+                                }
+                                umma_commit(bempty(bs));
+                                if (ky == kyn - 1 && kx == kyn - 1) umma_commit(aempty(as));
+                                if (kit == kiters - 1) umma_commit(xfull(xa));
+                            }
+                            __syncwarp();
+                            if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
+                        }
+                    }
+                    if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
+                }
             }
         }
     } else {
         // ------------------------------------------- promotion + epilogue ---------------------------------------------
         const int quad = warp & 3;
-        const int m = quad * 32 + lane;
-        const int px = m % Cfg::TW, py = m / Cfg::TW;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
         const int nchains = (kiters + promote - 1) / promote;
         uint32_t mcount = 0, tcount = 0;
@@ -238,30 +294,70 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 tc_fence_before();
                 mbar_arrive(xempty(xa));
             }
+            if (dbg != nullptr && threadIdx.x == 64) dbg[4] = clock64();
             const int tm = tile % tiles_m;
             const int tn = tile / tiles_m;
             const int tx = tm % p.tiles_x;
             const int ty = (tm / p.tiles_x) % p.tiles_y;
             const int fr = tm / (p.tiles_x * p.tiles_y);
-            const int x = tx * Cfg::TW + px, y = ty * Cfg::TH + py, n0 = tn * N_TILE;
-            if ((x < p.W) && (y < p.H)) {
-                const size_t pix = ((size_t)fr * p.H + y) * p.W + x;
-                const size_t obase = pix * (size_t)p.Cout + n0;
-                float alpha = p.alpha;
-                if (p.alpha_dev != nullptr) alpha *= __ldg(p.alpha_dev + (size_t)p.alpha_stride * fr);
+            const int n0 = tn * N_TILE;
+            const int m = quad * 32 + lane;                  // accumulator row == pixel inside the tile
+            float alpha = p.alpha;
+            if (p.alpha_dev != nullptr) alpha *= __ldg(p.alpha_dev + (size_t)p.alpha_stride * fr);
+            if (p.use_tma_store) {
+                // Plane outputs leave through shared memory and a TMA store: a "thread = pixel" register tile written
+                // directly to NHWC memory touches 32 different lines per warp instruction. Each thread writes its pixel's
+                // 64 channels (one 128-byte row, 16-byte chunks XOR-swizzled by the row index exactly as the tensor map's
+                // SWIZZLE_128B expects) and one elected thread stores the 16x8-pixel box; the image border is clipped by TMA.
 #pragma unroll
-                for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-                    float v[32];
+                for (int h0 = 0; h0 < N_TILE; h0 += 64) {
+                    if (threadIdx.x == 64) tma_store_wait_read();          // previous box has left the staging buffer
+                    named_bar_sync(1, 128);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = acc[c0 + j] * alpha;
-                    conv_epilogue_32(p, v, obase + c0, n0 + c0);
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = acc[h0 + c0 + j] * alpha;
+                        uint32_t hi[16], lo[16];
+                        conv_epilogue_regs_32(p, v, n0 + h0 + c0, hi, lo);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t chunk = (uint32_t)(((c0 >> 3) + q) ^ (m & 7));
+                            const uint32_t a = o_base + (uint32_t)m * 128u + chunk * 16u;
+                            st_shared_v4(a, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                            st_shared_v4(a + Cfg::OUT_PLANE, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);
+                    if (threadIdx.x == 64) {
+                        tma_store_4d(&tmO_hi, o_base, n0 + h0, tx * Cfg::TW, ty * Cfg::TH, fr);
+                        tma_store_4d(&tmO_lo, o_base + Cfg::OUT_PLANE, n0 + h0, tx * Cfg::TW, ty * Cfg::TH, fr);
+                        tma_store_commit();
+                    }
+                }
+            } else {
+                const int x = tx * Cfg::TW + (m % Cfg::TW), y = ty * Cfg::TH + (m / Cfg::TW);
+                if ((x < p.W) && (y < p.H)) {
+                    const size_t pix = ((size_t)fr * p.H + y) * p.W + x;
+                    const size_t obase = pix * (size_t)p.Cout + n0;
+#pragma unroll
+                    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = acc[c0 + j] * alpha;
+                        conv_epilogue_32(p, v, obase + c0, n0 + c0);
+                    }
                 }
             }
+            if (dbg != nullptr && threadIdx.x == 64) dbg[5] = clock64();
         }
+        if (p.use_tma_store && threadIdx.x == 64) tma_store_wait_all();
     }
 
     tc_fence_before();
     __syncthreads();
+    if (dbg != nullptr && threadIdx.x == 0) dbg[6] = clock64();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);

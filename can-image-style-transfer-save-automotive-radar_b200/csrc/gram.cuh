@@ -134,27 +134,26 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
             }
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
+                // MN-major SW128 descriptors: low word = start >> 4 | (LBO = 8192 B) >> 4 << 16, constant high word
                 const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
                 const uint32_t sB = diag ? sA : sA + 2 * Cfg::T_BYTES;
+                const uint32_t a_lo = (sA >> 4) | ((8192u >> 4) << 16);
+                const uint32_t b_lo = (sB >> 4) | ((8192u >> 4) << 16);
+                const uint32_t hi_w = (1024u >> 4) | (1u << 14) | (2u << 29);
                 const uint32_t d_main = tmem_base + mb * 128u;
                 const uint32_t d_cross = tmem_base + 256u;
+                const uint32_t idesc = p.idesc;
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {          // 16 pixels per MMA = two 8-row groups = 2048 B
-                    const uint64_t a_hi = umma_smem_desc_sw128(sA + k4 * 2048, 8192, 1024);
-                    const uint64_t b_hi = umma_smem_desc_sw128(sB + k4 * 2048, 8192, 1024);
-                    umma_f16(d_main, a_hi, b_hi, p.idesc, (in_chain | k4) != 0 ? 1u : 0u);
-                }
+                for (int k4 = 0; k4 < 4; ++k4)            // 16 pixels per MMA = two 8-row groups = 2048 B
+                    umma_f16_lh(d_main, a_lo + k4 * 128, hi_w, b_lo + k4 * 128, hi_w, idesc, (in_chain | k4) != 0 ? 1u : 0u);
                 if (in_chain == promote - 1 || kit == kiters - 1) umma_commit(mfull_bar(mb));
                 if (split3) {
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
-                        const uint64_t a_hi = umma_smem_desc_sw128(sA + k4 * 2048, 8192, 1024);
-                        const uint64_t b_hi = umma_smem_desc_sw128(sB + k4 * 2048, 8192, 1024);
-                        const uint64_t a_lo = umma_smem_desc_sw128(sA + Cfg::T_BYTES + k4 * 2048, 8192, 1024);
-                        const uint64_t b_lo = umma_smem_desc_sw128(sB + Cfg::T_BYTES + k4 * 2048, 8192, 1024);
-                        umma_f16(d_cross, a_hi, b_lo, p.idesc, (kit | k4) != 0 ? 1u : 0u);
-                        umma_f16(d_cross, a_lo, b_hi, p.idesc, 1u);
+                        umma_f16_lh(d_cross, a_lo + k4 * 128, hi_w, b_lo + (Cfg::T_BYTES >> 4) + k4 * 128, hi_w, idesc,
+                                    (kit | k4) != 0 ? 1u : 0u);
+                        umma_f16_lh(d_cross, a_lo + (Cfg::T_BYTES >> 4) + k4 * 128, hi_w, b_lo + k4 * 128, hi_w, idesc, 1u);
                     }
                 }
                 umma_commit(empty_bar(stage));

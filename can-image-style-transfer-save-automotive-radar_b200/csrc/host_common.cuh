@@ -13,6 +13,7 @@
 
 #include "../../include/ist_b200.h"
 #include "conv_igemm.cuh"
+#include "conv_halo.cuh"
 #include "elementwise.cuh"
 #include "gram.cuh"
 
@@ -126,14 +127,38 @@ inline int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
     return IST_OK;
 }
 
+// which implicit-GEMM kernel runs the convolutions: 1 = conv_halo.cuh (default), 0 = conv_igemm.cuh (IST_B200_CONV=igemm)
+inline int conv_impl_halo() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("IST_B200_CONV");
+        v = (e != nullptr && strcmp(e, "igemm") == 0) ? 0 : 1;
+    }
+    return v;
+}
+// timing experiments (results are garbage when loads are skipped): IST_B200_DBG_FLAGS bit 1 (2) skips the A loads, bit 2 (4) the B loads
+inline int halo_dbg_flags() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("IST_B200_DBG_FLAGS");
+        v = (e != nullptr) ? atoi(e) : 0;     // debug: bit 1 (2) skips the A loads, bit 2 (4) skips the B loads (timing experiments)
+    }
+    return v;
+}
 inline void pick_tile(int W, int* TW, int* TH) {
+    if (conv_impl_halo()) { *TW = 8; *TH = 16; return; }
     if (W >= 16) { *TW = 16; *TH = 8; } else { *TW = 8; *TH = 16; }
 }
-// NHWC planes [NB,H,W,C] as (C, W, H, NB), box (64, TW, TH, 1): the A operand of the implicit GEMM
-inline int map_act(CUtensorMap* m, const uint16_t* base, int NB, int H, int W, int C, int TW, int TH) {
+// NHWC planes [NB,H,W,C] as (C, W, H, NB): the A operand of the implicit GEMM for a `taps`-tap contraction.
+// conv_igemm: box (64, TW, TH, 1) fetched once per tap; conv_halo: box (64, TW+2, TH+2, 1) fetched once per 64-channel
+// chunk when taps == 9 (exact (64, TW, TH, 1) box for 1x1 contractions).
+inline int map_act(CUtensorMap* m, const uint16_t* base, int NB, int H, int W, int C, int taps) {
+    int TW, TH;
+    pick_tile(W, &TW, &TH);
+    const int halo = (conv_impl_halo() && taps == 9) ? 2 : 0;
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
     const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-    const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, 1};
+    const uint32_t box[4] = {64, (uint32_t)(TW + halo), (uint32_t)(TH + halo), 1};
     return make_tmap(m, base, 4, dims, strides, box);
 }
 // weight planes [G][N][K] as (K, N, G), box (64, n_tile, 1): the B operand (G = tap, or frame for the Gram backward)
@@ -175,6 +200,50 @@ inline int launch_conv_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
     IST_CUDA(cudaGetLastError());
     return IST_OK;
 }
+template <int N_TILE>
+inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                         const CUtensorMap& b_lo, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const ConvParams& p) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        IST_CUDA(cudaFuncSetAttribute(conv_halo_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      HaloCfg<N_TILE>::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int total = p.NB * p.tiles_x * p.tiles_y * p.tiles_n;
+    const int grid = total < num_sms() ? total : num_sms();
+    const double px = (double)p.NB * p.H * p.W;
+    const int planes = p.passes == 3 ? 2 : 1;
+    launch_pre(p.taps == 9 ? (p.mode == CONV_FWD ? "conv_halo_fwd" : "conv_halo_dgrad") : "conv_halo_gram_bwd",
+               2.0 * px * p.Cout * p.Cin * p.taps,
+               planes * 2.0 * (px * p.Cin + (double)p.taps * p.Cin * p.Cout) + px * p.Cout * 4.0, st);
+    static int dbg_on = -1;
+    if (dbg_on < 0) { const char* e = getenv("IST_B200_DBG_TIMES"); dbg_on = (e != nullptr && atoi(e) == 1) ? 1 : 0; }
+    if (dbg_on && !book().capturing) {
+        // phase stamps per CTA: 0 entry, 1 setup done, 2 first MMA issued, 3 last MMA of the last tile issued,
+        // 4 last tile's accumulators in registers, 5 last tile stored, 6 exit
+        static long long* dbuf = nullptr;
+        if (dbuf == nullptr) IST_CUDA(cudaMalloc(&dbuf, sizeof(long long) * 8 * 1024));
+        IST_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(long long) * 8 * 1024, st));
+        ConvParams q = p;
+        q.dbg_times = dbuf;
+        conv_halo_kernel<N_TILE><<<grid, 224, HaloCfg<N_TILE>::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, q);
+        IST_CUDA(cudaStreamSynchronize(st));
+        std::vector<long long> h(8 * (size_t)grid);
+        IST_CUDA(cudaMemcpy(h.data(), dbuf, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost));
+        double sum[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < grid; ++c)
+            for (int k = 1; k < 7; ++k) sum[k] += (double)(h[8 * c + k] - h[8 * c]);
+        fprintf(stderr, "[dbg] conv %dx%d %d->%d taps %d passes %d promote %d grid %d tiles %d | avg clk since entry: setup %.0f first_mma %.0f last_issue %.0f acc_read %.0f stored %.0f exit %.0f\n",
+                p.H, p.W, p.Cin, p.Cout, p.taps, p.passes, p.promote, grid, total, sum[1] / grid, sum[2] / grid, sum[3] / grid,
+                sum[4] / grid, sum[5] / grid, sum[6] / grid);
+        launch_post(st);
+        return IST_OK;
+    }
+    conv_halo_kernel<N_TILE><<<grid, 224, HaloCfg<N_TILE>::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, p);
+    launch_post(st);
+    IST_CUDA(cudaGetLastError());
+    return IST_OK;
+}
 inline int conv_n_tile(int cout) { return cout >= 128 ? 128 : 64; }
 // k-steps per tensor-core accumulation chain before promotion to fp32 registers (IST_B200_PROMOTE overrides; 1 = most accurate)
 inline int promote_steps() {
@@ -186,8 +255,11 @@ inline int promote_steps() {
     return v;
 }
 // Fills the tiling fields of p (NB,H,W,Cin,Cout,taps,passes,mode and epilogue pointers must be set) and launches.
+// o_hi / o_lo: optional tensor maps (map_act(..., taps = 1)) of the output planes; with them the conv_halo forward epilogue
+// leaves through shared memory + TMA store.
 inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-                       const CUtensorMap& b_lo, ConvParams p, bool bf16) {
+                       const CUtensorMap& b_lo, ConvParams p, bool bf16, const CUtensorMap* o_hi = nullptr,
+                       const CUtensorMap* o_lo = nullptr) {
     if (p.Cin % 64 != 0 || p.Cout % 64 != 0) return fail(IST_ERR_ARG, "conv_igemm needs Cin, Cout %% 64 == 0 (got %d, %d)", p.Cin, p.Cout);
     pick_tile(p.W, &p.TW, &p.TH);
     p.tiles_x = (p.W + p.TW - 1) / p.TW;
@@ -196,6 +268,13 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
     p.tiles_n = p.Cout / nt;
     if (p.promote < 1) p.promote = promote_steps();
     p.idesc = umma_idesc_f16(bf16 ? UMMA_FMT_BF16 : UMMA_FMT_F16, 128, nt, 0, 0);
+    if (conv_impl_halo()) {
+        p.dbg_flags = halo_dbg_flags();
+        p.use_tma_store = (p.mode == CONV_FWD && o_hi != nullptr && o_lo != nullptr) ? 1 : 0;
+        const CUtensorMap& oh = p.use_tma_store ? *o_hi : a_hi;
+        const CUtensorMap& ol = p.use_tma_store ? *o_lo : a_lo;
+        return nt == 128 ? launch_halo_t<128>(st, a_hi, a_lo, b_hi, b_lo, oh, ol, p) : launch_halo_t<64>(st, a_hi, a_lo, b_hi, b_lo, oh, ol, p);
+    }
     return nt == 128 ? launch_conv_t<128>(st, a_hi, a_lo, b_hi, b_lo, p) : launch_conv_t<64>(st, a_hi, a_lo, b_hi, b_lo, p);
 }
 

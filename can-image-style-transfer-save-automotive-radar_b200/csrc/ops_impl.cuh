@@ -71,18 +71,18 @@ int ist_op_conv3x3_relu_fwd(const float* x, const float* w, const float* b, floa
         IST_TRY(to_planes(st, x, ih, il, NB, cin, HW, kS, false));
         weight_repack_kernel<<<ew_grid(wn, 256), 256, 0, st>>>(w, cout, cin, ws, fh, fl, dh, dl);
         IST_CUDA(cudaGetLastError());
-        int TW, TH;
-        pick_tile(W, &TW, &TH);
-        CUtensorMap a_hi, a_lo, b_hi, b_lo;
-        IST_TRY(map_act(&a_hi, ih, NB, H, W, cin, TW, TH));
-        IST_TRY(map_act(&a_lo, il, NB, H, W, cin, TW, TH));
+        CUtensorMap a_hi, a_lo, b_hi, b_lo, o_hi, o_lo;
+        IST_TRY(map_act(&a_hi, ih, NB, H, W, cin, 9));
+        IST_TRY(map_act(&a_lo, il, NB, H, W, cin, 9));
+        IST_TRY(map_act(&o_hi, oh, NB, H, W, cout, 1));
+        IST_TRY(map_act(&o_lo, ol, NB, H, W, cout, 1));
         IST_TRY(map_b(&b_hi, fh, 9, cout, cin, conv_n_tile(cout)));
         IST_TRY(map_b(&b_lo, fl, 9, cout, cin, conv_n_tile(cout)));
         ConvParams p;
         memset(&p, 0, sizeof(p));
         p.NB = NB; p.H = H; p.W = W; p.Cin = cin; p.Cout = cout; p.taps = 9; p.passes = 3; p.mode = CONV_FWD;
         p.alpha = 1.f / (kS * ws); p.bias = b; p.out_scale = kS; p.out_hi = oh; p.out_lo = ol;
-        IST_TRY(launch_conv(st, a_hi, a_lo, b_hi, b_lo, p, false));
+        IST_TRY(launch_conv(st, a_hi, a_lo, b_hi, b_lo, p, false, &o_hi, &o_lo));
     }
     IST_TRY(from_planes(st, oh, ol, y, NB, cout, HW, 1.f / kS, false));
     return IST_OK;
@@ -112,11 +112,9 @@ int ist_op_conv3x3_dgrad(const float* dy, const float* w, float* dx, int NB, int
     IST_TRY(t.alloc(&o32, (size_t)NB * HW * cin));
     weight_repack_kernel<<<ew_grid(wn, 256), 256, 0, st>>>(w, cout, cin, 1.f, fh, fl, dh, dl);
     IST_CUDA(cudaGetLastError());
-    int TW, TH;
-    pick_tile(W, &TW, &TH);
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
-    IST_TRY(map_act(&a_hi, gh, NB, H, W, cout, TW, TH));
-    IST_TRY(map_act(&a_lo, gl, NB, H, W, cout, TW, TH));
+    IST_TRY(map_act(&a_hi, gh, NB, H, W, cout, 9));
+    IST_TRY(map_act(&a_lo, gl, NB, H, W, cout, 9));
     IST_TRY(map_b(&b_hi, dh, 9, cin, cout, conv_n_tile(cin)));
     IST_TRY(map_b(&b_lo, dl, 9, cin, cout, conv_n_tile(cin)));
     ConvParams p;
@@ -252,11 +250,9 @@ static int gram_common(const float* x, const float* target, float weight, float*
     gram_dmat_kernel<<<grid, 256, 0, st>>>(gp);
     IST_CUDA(cudaGetLastError());
     IST_TRY(t.alloc(&o32, (size_t)NB * HW * C));
-    int TW, TH;
-    pick_tile(W, &TW, &TH);
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
-    IST_TRY(map_act(&a_hi, fh, NB, H, W, C, TW, TH));
-    IST_TRY(map_act(&a_lo, fl, NB, H, W, C, TW, TH));
+    IST_TRY(map_act(&a_hi, fh, NB, H, W, C, 1));
+    IST_TRY(map_act(&a_lo, fl, NB, H, W, C, 1));
     IST_TRY(map_b(&b_hi, dh, NB, C, C, conv_n_tile(C)));
     IST_TRY(map_b(&b_lo, dl, NB, C, C, conv_n_tile(C)));
     ConvParams p;

@@ -35,6 +35,7 @@ struct Layer {
     CUtensorMap mBf_hi, mBf_lo;    // forward B
     CUtensorMap mBd_hi, mBd_lo;    // dgrad B
     CUtensorMap mG_hi, mG_lo;      // dgrad A: dY planes of this conv
+    CUtensorMap mO_hi, mO_lo;      // forward output planes (TMA-store epilogue)
     Planes dY;                     // bf16 planes, gradient w.r.t. this conv's pre-activation
     // feature-as-operand maps (Gram forward / Gram backward)
     CUtensorMap mGram_hi, mGram_lo, mFeat_hi, mFeat_lo, mD_hi, mD_lo;
@@ -113,7 +114,7 @@ int run_forward(ist_plan* P, const float* x, int upto, cudaStream_t st) {
                 p.bias = L.bias;
                 p.out_scale = kActScale;
                 p.out_hi = L.out.hi; p.out_lo = L.out.lo;
-                IST_TRY(launch_conv(st, L.mA_hi, L.mA_lo, L.mBf_hi, L.mBf_lo, p, false));
+                IST_TRY(launch_conv(st, L.mA_hi, L.mA_lo, L.mBf_hi, L.mBf_lo, p, false, &L.mO_hi, &L.mO_lo));
             }
         } else {
             const Layer& I = P->layers[l - 1];
@@ -166,10 +167,8 @@ int ensure_gram_buffers(ist_plan* P, Layer& L) {
     IST_TRY(P->mem.alloc(&L.d_lo, (size_t)P->NB * CC));
     IST_TRY(map_gram(&L.mGram_hi, L.out.hi, P->NB, L.H * L.W, L.C));
     IST_TRY(map_gram(&L.mGram_lo, L.out.lo, P->NB, L.H * L.W, L.C));
-    int TW, TH;
-    pick_tile(L.W, &TW, &TH);
-    IST_TRY(map_act(&L.mFeat_hi, L.out.hi, P->NB, L.H, L.W, L.C, TW, TH));
-    IST_TRY(map_act(&L.mFeat_lo, L.out.lo, P->NB, L.H, L.W, L.C, TW, TH));
+    IST_TRY(map_act(&L.mFeat_hi, L.out.hi, P->NB, L.H, L.W, L.C, 1));
+    IST_TRY(map_act(&L.mFeat_lo, L.out.lo, P->NB, L.H, L.W, L.C, 1));
     IST_TRY(map_b(&L.mD_hi, L.d_hi, P->NB, L.C, L.C, conv_n_tile(L.C)));
     IST_TRY(map_b(&L.mD_lo, L.d_lo, P->NB, L.C, L.C, conv_n_tile(L.C)));
     return IST_OK;
@@ -447,17 +446,17 @@ int ist_plan_create(ist_plan** out, int n_layers, const ist_layer_desc* layers, 
         if (rc == IST_OK) rc = P->mem.alloc(&L.wf_lo, wn);
         if (rc == IST_OK) rc = P->mem.alloc(&L.wd_hi, wn);
         if (rc == IST_OK) rc = P->mem.alloc(&L.wd_lo, wn);
-        int TW, TH;
-        pick_tile(L.W, &TW, &TH);
         const Layer& I = P->layers[l - 1];
-        if (rc == IST_OK) rc = map_act(&L.mA_hi, I.out.hi, batch, L.H, L.W, L.cin, TW, TH);
-        if (rc == IST_OK) rc = map_act(&L.mA_lo, I.out.lo, batch, L.H, L.W, L.cin, TW, TH);
+        if (rc == IST_OK) rc = map_act(&L.mA_hi, I.out.hi, batch, L.H, L.W, L.cin, 9);
+        if (rc == IST_OK) rc = map_act(&L.mA_lo, I.out.lo, batch, L.H, L.W, L.cin, 9);
         if (rc == IST_OK) rc = map_b(&L.mBf_hi, L.wf_hi, 9, L.cout, L.cin, conv_n_tile(L.cout));
         if (rc == IST_OK) rc = map_b(&L.mBf_lo, L.wf_lo, 9, L.cout, L.cin, conv_n_tile(L.cout));
         if (rc == IST_OK) rc = map_b(&L.mBd_hi, L.wd_hi, 9, L.cin, L.cout, conv_n_tile(L.cin));
         if (rc == IST_OK) rc = map_b(&L.mBd_lo, L.wd_lo, 9, L.cin, L.cout, conv_n_tile(L.cin));
-        if (rc == IST_OK) rc = map_act(&L.mG_hi, L.dY.hi, batch, L.H, L.W, L.cout, TW, TH);
-        if (rc == IST_OK) rc = map_act(&L.mG_lo, L.dY.lo, batch, L.H, L.W, L.cout, TW, TH);
+        if (rc == IST_OK) rc = map_act(&L.mO_hi, L.out.hi, batch, L.H, L.W, L.cout, 1);
+        if (rc == IST_OK) rc = map_act(&L.mO_lo, L.out.lo, batch, L.H, L.W, L.cout, 1);
+        if (rc == IST_OK) rc = map_act(&L.mG_hi, L.dY.hi, batch, L.H, L.W, L.cout, 9);
+        if (rc == IST_OK) rc = map_act(&L.mG_lo, L.dY.lo, batch, L.H, L.W, L.cout, 9);
     }
     if (rc != IST_OK) {
         delete P;
