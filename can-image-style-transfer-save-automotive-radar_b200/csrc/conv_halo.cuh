@@ -57,6 +57,61 @@ __device__ __forceinline__ void conv_epilogue_regs_32(const ConvParams& p, const
     }
 }
 
+// Data-gradient epilogue on registers for 32 consecutive channels of one pixel (element offset `o`): adds the optional
+// fp32 addend and content term, applies the ReLU mask, and splits into bf16 hi / lo packs (same arithmetic and order as
+// the CONV_GRAD branch of conv_epilogue_32). `valid` = the pixel lies inside the image (no loads otherwise).
+__device__ __forceinline__ void conv_grad_regs_32(const ConvParams& p, float (&v)[32], size_t o, bool valid, uint32_t (&hi)[16],
+                                                  uint32_t (&lo)[16]) {
+    if (valid) {
+        if (p.addend != nullptr) {
+            const float4* ad = reinterpret_cast<const float4*>(p.addend + o);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 t = __ldg(ad + q);
+                v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+            }
+        }
+        if (p.f_hi != nullptr) {
+            const uint4* fh = reinterpret_cast<const uint4*>(p.f_hi + o);
+            const uint4* fl = reinterpret_cast<const uint4*>(p.f_lo + o);
+            const uint4* th = reinterpret_cast<const uint4*>(p.t_hi + o);
+            const uint4* tl = reinterpret_cast<const uint4*>(p.t_lo + o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 a = __ldg(fh + q), b = __ldg(fl + q), c = __ldg(th + q), d = __ldg(tl + q);
+                const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
+                const uint32_t uc[4] = {c.x, c.y, c.z, c.w}, ud[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float d0 = (h_lo_f(ua[e]) - h_lo_f(uc[e])) + (h_lo_f(ub[e]) - h_lo_f(ud[e]));
+                    const float d1 = (h_hi_f(ua[e]) - h_hi_f(uc[e])) + (h_hi_f(ub[e]) - h_hi_f(ud[e]));
+                    v[8 * q + 2 * e] += p.content_coef * d0;
+                    v[8 * q + 2 * e + 1] += p.content_coef * d1;
+                }
+            }
+        }
+        if (p.mask_hi != nullptr) {
+            const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 a = __ldg(mk + q);
+                const uint32_t ua[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (!(h_lo_f(ua[e]) > 0.f)) v[8 * q + 2 * e] = 0.f;
+                    if (!(h_hi_f(ua[e]) > 0.f)) v[8 * q + 2 * e + 1] = 0.f;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        const uint32_t h = pack_bf2(v[j], v[j + 1]);
+        hi[j >> 1] = h;
+        lo[j >> 1] = pack_bf2(v[j] - bf_lo_f(h), v[j + 1] - bf_hi_f(h));
+    }
+}
+
 template <int N_TILE>
 __global__ void __launch_bounds__(224, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -304,6 +359,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const int m = quad * 32 + lane;                  // accumulator row == pixel inside the tile
             float alpha = p.alpha;
             if (p.alpha_dev != nullptr) alpha *= __ldg(p.alpha_dev + (size_t)p.alpha_stride * fr);
+            const int gx = tx * Cfg::TW + (m % Cfg::TW), gy = ty * Cfg::TH + (m / Cfg::TW);
+            const bool gvalid = (gx < p.W) && (gy < p.H);
+            const size_t gpix = ((size_t)fr * p.H + (gvalid ? gy : 0)) * p.W + (gvalid ? gx : 0);
             if (p.use_tma_store) {
                 // Plane outputs leave through shared memory and a TMA store: a "thread = pixel" register tile written
                 // directly to NHWC memory touches 32 different lines per warp instruction. Each thread writes its pixel's
@@ -319,7 +377,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = acc[h0 + c0 + j] * alpha;
                         uint32_t hi[16], lo[16];
-                        conv_epilogue_regs_32(p, v, n0 + h0 + c0, hi, lo);
+                        if (p.mode == CONV_FWD) conv_epilogue_regs_32(p, v, n0 + h0 + c0, hi, lo);
+                        else conv_grad_regs_32(p, v, gpix * (size_t)p.Cout + n0 + h0 + c0, gvalid, hi, lo);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const uint32_t chunk = (uint32_t)(((c0 >> 3) + q) ^ (m & 7));
@@ -337,10 +396,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     }
                 }
             } else {
-                const int x = tx * Cfg::TW + (m % Cfg::TW), y = ty * Cfg::TH + (m / Cfg::TW);
-                if ((x < p.W) && (y < p.H)) {
-                    const size_t pix = ((size_t)fr * p.H + y) * p.W + x;
-                    const size_t obase = pix * (size_t)p.Cout + n0;
+                if (gvalid) {
+                    const size_t obase = gpix * (size_t)p.Cout + n0;
 #pragma unroll
                     for (int c0 = 0; c0 < N_TILE; c0 += 32) {
                         float v[32];

@@ -270,7 +270,7 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
     p.idesc = umma_idesc_f16(bf16 ? UMMA_FMT_BF16 : UMMA_FMT_F16, 128, nt, 0, 0);
     if (conv_impl_halo()) {
         p.dbg_flags = halo_dbg_flags();
-        p.use_tma_store = (p.mode == CONV_FWD && o_hi != nullptr && o_lo != nullptr) ? 1 : 0;
+        p.use_tma_store = (p.out_f32 == nullptr && o_hi != nullptr && o_lo != nullptr) ? 1 : 0;
         const CUtensorMap& oh = p.use_tma_store ? *o_hi : a_hi;
         const CUtensorMap& ol = p.use_tma_store ? *o_lo : a_lo;
         return nt == 128 ? launch_halo_t<128>(st, a_hi, a_lo, b_hi, b_lo, oh, ol, p) : launch_halo_t<64>(st, a_hi, a_lo, b_hi, b_lo, oh, ol, p);

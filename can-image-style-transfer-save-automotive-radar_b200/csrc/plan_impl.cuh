@@ -36,6 +36,7 @@ struct Layer {
     CUtensorMap mBd_hi, mBd_lo;    // dgrad B
     CUtensorMap mG_hi, mG_lo;      // dgrad A: dY planes of this conv
     CUtensorMap mO_hi, mO_lo;      // forward output planes (TMA-store epilogue)
+    CUtensorMap mGo_hi, mGo_lo;    // dY planes of this conv as a TMA-store destination (written by the producer of the gradient)
     Planes dY;                     // bf16 planes, gradient w.r.t. this conv's pre-activation
     // feature-as-operand maps (Gram forward / Gram backward)
     CUtensorMap mGram_hi, mGram_lo, mFeat_hi, mFeat_lo, mD_hi, mD_lo;
@@ -193,10 +194,11 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         *coef = (float)(2.0 * L.content_w / ((double)L.C * L.H * L.W * kActScale));
     };
     // dgrad of conv `cj` (layer index) into the gradient of its input tensor
-    auto dgrad = [&](const Layer& Cj, ConvParams p) -> int {
+    auto dgrad = [&](const Layer& Cj, ConvParams p, const Layer* dst) -> int {
         p.NB = NB; p.H = Cj.H; p.W = Cj.W; p.Cin = Cj.cout; p.Cout = Cj.cin; p.taps = 9;
         p.passes = P->passes_bwd; p.mode = CONV_GRAD; p.alpha = 1.f;
-        return launch_conv(st, Cj.mG_hi, Cj.mG_lo, Cj.mBd_hi, Cj.mBd_lo, p, true);
+        return launch_conv(st, Cj.mG_hi, Cj.mG_lo, Cj.mBd_hi, Cj.mBd_lo, p, true, dst != nullptr ? &dst->mGo_hi : nullptr,
+                           dst != nullptr ? &dst->mGo_lo : nullptr);
     };
     auto gram_bwd = [&](Layer& L, const float* addend, bool content) -> int {
         ConvParams p;
@@ -208,7 +210,7 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         if (content) set_content(L, &p.f_hi, &p.f_lo, &p.t_hi, &p.t_lo, &p.content_coef);
         p.mask_hi = L.out.hi;
         p.out_hi = L.dY.hi; p.out_lo = L.dY.lo;
-        return launch_conv(st, L.mFeat_hi, L.mFeat_lo, L.mD_hi, L.mD_lo, p, false);
+        return launch_conv(st, L.mFeat_hi, L.mFeat_lo, L.mD_hi, L.mD_lo, p, false, &L.mGo_hi, &L.mGo_lo);
     };
     auto route = [&](Layer& L, const float* g_pool, const float* addend, bool content, bool to_f32, float* f32_out) -> int {
         RouteParams r;
@@ -245,12 +247,12 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
             if (content) set_content(L, &p.f_hi, &p.f_lo, &p.t_hi, &p.t_lo, &p.content_coef);
             if (style) {
                 p.out_f32 = P->fbuf[1];
-                IST_TRY(dgrad(Cn, p));
+                IST_TRY(dgrad(Cn, p, nullptr));
                 IST_TRY(gram_bwd(L, P->fbuf[1], false));
             } else {
                 p.mask_hi = L.out.hi;
                 p.out_hi = L.dY.hi; p.out_lo = L.dY.lo;
-                IST_TRY(dgrad(Cn, p));
+                IST_TRY(dgrad(Cn, p, &L));
             }
         } else if (has_up) {
             // consumer is a pool; the pool's consumer (if any) is conv l+2
@@ -263,7 +265,7 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
                 memset(&p, 0, sizeof(p));
                 p.addend = ext(Pl);
                 p.out_f32 = P->fbuf[0];
-                IST_TRY(dgrad(Cn, p));
+                IST_TRY(dgrad(Cn, p, nullptr));
                 g_pool = P->fbuf[0];
             } else {
                 g_pool = ext(Pl);
@@ -439,6 +441,8 @@ int ist_plan_create(ist_plan** out, int n_layers, const ist_layer_desc* layers, 
         if (rc != IST_OK) break;
         if (l == 0) {
             rc = P->mem.alloc(&L.w_f32, (size_t)L.cout * L.cin * 9);
+            if (rc == IST_OK) rc = map_act(&L.mGo_hi, L.dY.hi, batch, L.H, L.W, L.cout, 1);
+            if (rc == IST_OK) rc = map_act(&L.mGo_lo, L.dY.lo, batch, L.H, L.W, L.cout, 1);
             continue;
         }
         const size_t wn = (size_t)L.cout * L.cin * 9;
@@ -455,6 +459,8 @@ int ist_plan_create(ist_plan** out, int n_layers, const ist_layer_desc* layers, 
         if (rc == IST_OK) rc = map_b(&L.mBd_lo, L.wd_lo, 9, L.cin, L.cout, conv_n_tile(L.cin));
         if (rc == IST_OK) rc = map_act(&L.mO_hi, L.out.hi, batch, L.H, L.W, L.cout, 1);
         if (rc == IST_OK) rc = map_act(&L.mO_lo, L.out.lo, batch, L.H, L.W, L.cout, 1);
+        if (rc == IST_OK) rc = map_act(&L.mGo_hi, L.dY.hi, batch, L.H, L.W, L.cout, 1);
+        if (rc == IST_OK) rc = map_act(&L.mGo_lo, L.dY.lo, batch, L.H, L.W, L.cout, 1);
         if (rc == IST_OK) rc = map_act(&L.mG_hi, L.dY.hi, batch, L.H, L.W, L.cout, 9);
         if (rc == IST_OK) rc = map_act(&L.mG_lo, L.dY.lo, batch, L.H, L.W, L.cout, 9);
     }
