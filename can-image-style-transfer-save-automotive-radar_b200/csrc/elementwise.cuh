@@ -213,52 +213,93 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /
 
 // Data-gradient of the first conv: dX[ci,y,x] = sum_{co,ky,kx} W[co,ci,ky,kx] * dY[co, y-ky+1, x-kx+1].
 // dY = bf16 planes already masked by relu1_1; output = fp32 NCHW image gradient (x.grad of utils.py:36).
+// N = 3 output channels is no tensor-core shape, so this is a register-tiled CUDA-core kernel: a block owns a 32 x 16
+// pixel tile, stages the (34 x 18)-pixel halo of dY for 16 channels at a time in shared memory as fp32 (hi + lo summed
+// once instead of once per tap), and every thread produces 4 consecutive pixels x 3 channels, so that per (co, ky) it
+// issues 2 shared loads of dY and 3 broadcast loads of weights for 36 FMAs.
+constexpr int CFD_TX = 32, CFD_TY = 16, CFD_HX = 36 /* 34 padded to a multiple of 4 */, CFD_HY = 18, CFD_CO = 16;
+constexpr int CFD_SMEM = (CFD_CO * CFD_HY * CFD_HX + 64 * 9 * 4) * 4;
+
 template <int COUT>
 __global__ void __launch_bounds__(128)
 conv_first_dgrad_kernel(const uint16_t* __restrict__ g_hi, const uint16_t* __restrict__ g_lo,
                         const float* __restrict__ w /*[COUT][3][3][3]*/, float* __restrict__ grad, int NB, int H, int W) {
-    __shared__ float ws[9][COUT][3];
-    for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
-        const int co = i / 27, r = i % 27, ci = r / 9, tap = r % 9;
-        ws[tap][co][ci] = w[i];
+    extern __shared__ __align__(16) float cfd_smem[];
+    float* sd = cfd_smem;                                   // [CFD_CO][CFD_HY][CFD_HX]
+    float4* ws = reinterpret_cast<float4*>(cfd_smem + CFD_CO * CFD_HY * CFD_HX);   // [COUT][9] (ci in .x .y .z)
+    const int tid = threadIdx.x;
+    for (int i = tid; i < COUT * 9; i += blockDim.x) {
+        const int co = i / 9, tap = i % 9;
+        ws[i] = make_float4(w[(co * 3 + 0) * 9 + tap], w[(co * 3 + 1) * 9 + tap], w[(co * 3 + 2) * 9 + tap], 0.f);
     }
-    __syncthreads();
-    const size_t HW = (size_t)H * W;
-    const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (gid >= (size_t)NB * HW) return;
-    const int n = (int)(gid / HW);
-    const int pix = (int)(gid % HW);
-    const int y = pix / W, xx = pix % W;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll 1
-    for (int tap = 0; tap < 9; ++tap) {
-        const int ky = tap / 3, kx = tap % 3;
-        const int yy = y - ky + 1, xq = xx - kx + 1;
-        if (yy < 0 || yy >= H || xq < 0 || xq >= W) continue;
-        const size_t o = (((size_t)n * H + yy) * W + xq) * COUT;
-        const uint4* ph = reinterpret_cast<const uint4*>(g_hi + o);
-        const uint4* pl = reinterpret_cast<const uint4*>(g_lo + o);
+    const int n = blockIdx.z;
+    const int x0 = blockIdx.x * CFD_TX, y0 = blockIdx.y * CFD_TY;
+    const int lx0 = (tid & 7) * 4, ly = tid >> 3;
+    float acc[4][3];
 #pragma unroll
-        for (int q = 0; q < COUT / 8; ++q) {
-            const uint4 h = __ldg(ph + q), l = __ldg(pl + q);
-            const uint32_t uh[4] = {h.x, h.y, h.z, h.w}, ul[4] = {l.x, l.y, l.z, l.w};
+    for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; }
+    for (int c0 = 0; c0 < COUT; c0 += CFD_CO) {
+        __syncthreads();
+        for (int hp = tid; hp < CFD_HY * 34; hp += blockDim.x) {
+            const int hy = hp / 34, hx = hp % 34;
+            const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+            float v[CFD_CO];
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                const size_t o = ((((size_t)n * H + gy) * W + gx) * COUT + c0) / 8;
+                const uint4* ph = reinterpret_cast<const uint4*>(g_hi) + o;
+                const uint4* pl = reinterpret_cast<const uint4*>(g_lo) + o;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float va, vb;
-                unpack_sum<true>(uh[e], ul[e], va, vb);
-                const int co = q * 8 + 2 * e;
-                a0 = fmaf(va, ws[tap][co][0], a0);
-                a1 = fmaf(va, ws[tap][co][1], a1);
-                a2 = fmaf(va, ws[tap][co][2], a2);
-                a0 = fmaf(vb, ws[tap][co + 1][0], a0);
-                a1 = fmaf(vb, ws[tap][co + 1][1], a1);
-                a2 = fmaf(vb, ws[tap][co + 1][2], a2);
+                for (int q = 0; q < CFD_CO / 8; ++q) {
+                    const uint4 h = __ldg(ph + q), l = __ldg(pl + q);
+                    const uint32_t uh[4] = {h.x, h.y, h.z, h.w}, ul[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) unpack_sum<true>(uh[e], ul[e], v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CFD_CO; ++c) v[c] = 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < CFD_CO; ++c) sd[(c * CFD_HY + hy) * CFD_HX + hx] = v[c];
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int c = 0; c < CFD_CO; ++c) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                // halo row of dY that tap ky of output row ly reads: (y - ky + 1) - (y0 - 1) = ly - ky + 2
+                const float* row = sd + (c * CFD_HY + (ly - ky + 2)) * CFD_HX + lx0;
+                const float4 d0 = *reinterpret_cast<const float4*>(row);
+                const float2 d1 = *reinterpret_cast<const float2*>(row + 4);
+                const float d[6] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y};
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 wv = ws[(c0 + c) * 9 + ky * 3 + kx];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float dv = d[i - kx + 2];         // halo column (x - kx + 1) - (x0 - 1) - lx0
+                        acc[i][0] = fmaf(dv, wv.x, acc[i][0]);
+                        acc[i][1] = fmaf(dv, wv.y, acc[i][1]);
+                        acc[i][2] = fmaf(dv, wv.z, acc[i][2]);
+                    }
+                }
             }
         }
     }
-    grad[((size_t)n * 3 + 0) * HW + pix] = a0;
-    grad[((size_t)n * 3 + 1) * HW + pix] = a1;
-    grad[((size_t)n * 3 + 2) * HW + pix] = a2;
+    const int y = y0 + ly, x = x0 + lx0;
+    if (y >= H || x >= W) return;
+    const size_t HW = (size_t)H * W;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+        float* dst = grad + ((size_t)n * 3 + ci) * HW + (size_t)y * W + x;
+        if (x + 3 < W && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            *reinterpret_cast<float4*>(dst) = make_float4(acc[0][ci], acc[1][ci], acc[2][ci], acc[3][ci]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (x + i < W) dst[i] = acc[i][ci];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------

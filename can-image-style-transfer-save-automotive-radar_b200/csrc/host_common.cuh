@@ -278,6 +278,22 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
     return nt == 128 ? launch_conv_t<128>(st, a_hi, a_lo, b_hi, b_lo, p) : launch_conv_t<64>(st, a_hi, a_lo, b_hi, b_lo, p);
 }
 
+inline int launch_conv_first_dgrad(cudaStream_t st, const uint16_t* g_hi, const uint16_t* g_lo, const float* w, float* grad, int NB,
+                                   int H, int W) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        IST_CUDA(cudaFuncSetAttribute(conv_first_dgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFD_SMEM));
+        attr_done = true;
+    }
+    const double px = (double)NB * H * W;
+    launch_pre("conv_first_dgrad", 2.0 * px * 64 * 27, px * (12.0 + 256.0), st);
+    dim3 grid((W + CFD_TX - 1) / CFD_TX, (H + CFD_TY - 1) / CFD_TY, NB);
+    conv_first_dgrad_kernel<64><<<grid, 128, CFD_SMEM, st>>>(g_hi, g_lo, w, grad, NB, H, W);
+    launch_post(st);
+    IST_CUDA(cudaGetLastError());
+    return IST_OK;
+}
+
 inline void gram_split_plan(int NB, int HW, int C, int* splits, int* chunks_per_split) {
     const int tiles_c = (C + 127) / 128;
     const int tri = tiles_c * (tiles_c + 1) / 2;

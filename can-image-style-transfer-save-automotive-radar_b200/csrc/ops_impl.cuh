@@ -100,10 +100,7 @@ int ist_op_conv3x3_dgrad(const float* dy, const float* w, float* dx, int NB, int
     IST_TRY(to_planes(st, dy, gh, gl, NB, cout, HW, 1.f, true));
     if (cin == 3) {
         if (cout != 64) return fail(IST_ERR_ARG, "first-layer kernel is built for cout == 64");
-        const size_t px = (size_t)NB * HW;
-        conv_first_dgrad_kernel<64><<<(unsigned)((px + 127) / 128), 128, 0, st>>>(gh, gl, w, dx, NB, H, W);
-        IST_CUDA(cudaGetLastError());
-        return IST_OK;
+        return launch_conv_first_dgrad(st, gh, gl, w, dx, NB, H, W);
     }
     uint16_t *fh, *fl, *dh, *dl;
     float* o32;

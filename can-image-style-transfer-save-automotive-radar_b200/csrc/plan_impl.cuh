@@ -285,11 +285,7 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         }
     }
     Layer& L0 = P->layers[0];
-    const size_t px = (size_t)NB * L0.H * L0.W;
-    launch_pre("conv_first_dgrad", 2.0 * px * 64 * 27, px * (12.0 + 256.0), st);
-    conv_first_dgrad_kernel<64><<<(unsigned)((px + 127) / 128), 128, 0, st>>>(L0.dY.hi, L0.dY.lo, L0.w_f32, grad, NB, L0.H, L0.W);
-    launch_post(st);
-    IST_CUDA(cudaGetLastError());
+    IST_TRY(launch_conv_first_dgrad(st, L0.dY.hi, L0.dY.lo, L0.w_f32, grad, NB, L0.H, L0.W));
     return IST_OK;
 }
 
