@@ -117,6 +117,8 @@ __global__ void __launch_bounds__(224, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                  const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
+                 const __grid_constant__ CUtensorMap tmF_hi, const __grid_constant__ CUtensorMap tmF_lo,
+                 const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CUtensorMap tmD_lo,
                  const ConvParams p) {
     using Cfg = HaloCfg<N_TILE>;
     extern __shared__ uint8_t smem_raw[];
@@ -174,6 +176,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int total_tiles = tiles_m * p.tiles_n;
     const int cchunks = p.Cin >> 6;
     const int taps = p.taps;
+    // Fused Gram backward (style layers): after the taps * cchunks k-steps of the convolution, `extra_chunks` more k-steps
+    // compute D * F of this layer (A = the layer's feature planes, halo box, centre tap; B = the per-frame matrix
+    // D = ((G - A) + (G - A)^T) * 2^e as fp16 planes; instruction descriptor idesc2) into their own tensor-memory accumulator
+    // (the second cross buffer, so the cross terms are single-buffered in that case). Operand formats cannot be mixed inside
+    // one MMA and the two products carry different scales, so the sum is formed in the epilogue: acc += alpha2[frame] * gram.
+    const int xchunks = p.extra_chunks;
     const int kiters = taps * cchunks;
     const int promote = p.promote < 1 ? 1 : p.promote;
     const bool split = (p.passes == 3);
@@ -195,23 +203,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 const int ty = (tm / p.tiles_x) % p.tiles_y;
                 const int fr = tm / (p.tiles_x * p.tiles_y);
                 const int x0 = tx * Cfg::TW - (halo ? 1 : 0), y0 = ty * Cfg::TH - (halo ? 1 : 0), n0 = tn * N_TILE;
-                for (int cc = 0; cc < cchunks; ++cc) {
+                for (int cc = 0; cc < cchunks + xchunks; ++cc) {
+                    const bool ex = cc >= cchunks;
+                    const int c64 = (ex ? cc - cchunks : cc) * 64;
                     mbar_wait(aempty(as), aph ^ 1u);
                     const uint32_t sA = a_base + as * Cfg::A_STAGE;
                     if (p.dbg_flags & 2) { mbar_arrive(afull(as)); } else {
                     mbar_arrive_expect_tx(afull(as), a_tx);
-                    tma_load_4d(sA, &tmA_hi, afull(as), cc * 64, x0, y0, fr);
-                    if (split) tma_load_4d(sA + Cfg::A_PLANE, &tmA_lo, afull(as), cc * 64, x0, y0, fr);
+                    tma_load_4d(sA, ex ? &tmF_hi : &tmA_hi, afull(as), c64, x0, y0, fr);
+                    if (split) tma_load_4d(sA + Cfg::A_PLANE, ex ? &tmF_lo : &tmA_lo, afull(as), c64, x0, y0, fr);
                     }
                     if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
-                    for (int tap = 0; tap < taps; ++tap) {
-                        const int bz = p.b_frame ? fr : tap;
+                    const int ntap = ex ? 1 : taps;
+                    for (int tap = 0; tap < ntap; ++tap) {
+                        const int bz = (p.b_frame || ex) ? fr : tap;
                         mbar_wait(bempty(bs), bph ^ 1u);
                         const uint32_t sB = b_base + bs * Cfg::B_STAGE;
                         if (p.dbg_flags & 4) { mbar_arrive(bfull(bs)); } else {
                         mbar_arrive_expect_tx(bfull(bs), b_tx);
-                        tma_load_3d(sB, &tmB_hi, bfull(bs), cc * 64, n0, bz);
-                        if (split) tma_load_3d(sB + Cfg::B_PLANE, &tmB_lo, bfull(bs), cc * 64, n0, bz);
+                        tma_load_3d(sB, ex ? &tmD_hi : &tmB_hi, bfull(bs), c64, n0, bz);
+                        if (split) tma_load_3d(sB + Cfg::B_PLANE, ex ? &tmD_lo : &tmB_lo, bfull(bs), c64, n0, bz);
                         }
                         if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                     }
@@ -239,6 +250,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 const uint32_t a_lo_stage = (a_base + as * Cfg::A_STAGE) >> 4;
                 for (int ky = 0; ky < kyn; ++ky) {
                     for (int kx = 0; kx < kyn; ++kx, ++kit) {
+                        const bool last_tap = (ky == kyn - 1 && kx == kyn - 1);
                         const int in_chain = kit % promote;
                         const uint32_t mb = mcount & 1u;
                         const bool chain_end = (in_chain == promote - 1) || (kit == kiters - 1);
@@ -255,7 +267,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                                 umma_f16_lh(d_main, a_lo + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, (in_chain | k4) != 0 ? 1u : 0u);
                             if (chain_end) umma_commit(mfull(mb));
                             umma_commit(bempty(bs));
-                            if (ky == kyn - 1 && kx == kyn - 1) umma_commit(aempty(as));
+                            if (last_tap) umma_commit(aempty(as));
                             if (dbg != nullptr && kit == kiters - 1) dbg[3] = clock64();
                         }
                         __syncwarp();
@@ -263,6 +275,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                     }
                 }
+                if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
+            }
+            // fused Gram k-steps are issued by warp 6 alone; this warp only keeps the stage rings in step and contributes
+            // its share of the release arrivals
+            for (int xc = 0; xc < xchunks; ++xc) {
+                mbar_wait(afull(as), aph);
+                mbar_wait(bfull(bs), bph);
+                if (elect_one()) {
+                    mbar_arrive(bempty(bs));
+                    mbar_arrive(aempty(as));
+                }
+                __syncwarp();
+                if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                 if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
             }
         }
@@ -276,16 +301,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
             uint32_t tcount = 0;
+            const bool xsingle = xchunks > 0;         // single cross buffer when the second one holds the Gram accumulator
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-                const uint32_t xa = tcount & 1u;
+                const uint32_t xa = xsingle ? 0u : (tcount & 1u);
+                const uint32_t xph = xsingle ? (tcount & 1u) : ((tcount >> 1) & 1u);
                 const uint32_t d_cross = tmem_base + (uint32_t)(2 * N_TILE) + xa * N_TILE;
-                mbar_wait(xempty(xa), ((tcount >> 1) & 1u) ^ 1u);
+                const uint32_t d_gram = tmem_base + (uint32_t)(3 * N_TILE);
+                mbar_wait(xempty(xa), xph ^ 1u);
+                tc_fence_after();
                 int kit = 0;
                 for (int cc = 0; cc < cchunks; ++cc) {
                     mbar_wait(afull(as), aph);
                     const uint32_t a_lo_stage = (a_base + as * Cfg::A_STAGE) >> 4;
                     for (int ky = 0; ky < kyn; ++ky) {
                         for (int kx = 0; kx < kyn; ++kx, ++kit) {
+                            const bool last_tap = (ky == kyn - 1 && kx == kyn - 1);
                             mbar_wait(bfull(bs), bph);
                             tc_fence_after();
                             if (elect_one()) {
@@ -298,13 +328,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                                     umma_f16_lh(d_cross, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, 1u);
                                 }
                                 umma_commit(bempty(bs));
-                                if (ky == kyn - 1 && kx == kyn - 1) umma_commit(aempty(as));
-                                if (kit == kiters - 1) umma_commit(xfull(xa));
+                                if (last_tap) umma_commit(aempty(as));
+                                if (kit == kiters - 1 && xchunks == 0) umma_commit(xfull(xa));
                             }
                             __syncwarp();
                             if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                         }
                     }
+                    if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
+                }
+                for (int xc = 0; xc < xchunks; ++xc) {
+                    mbar_wait(afull(as), aph);
+                    mbar_wait(bfull(bs), bph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_lo = ((a_base + as * Cfg::A_STAGE) >> 4) + (uint32_t)((Cfg::PW + 1) * 8);   // centre tap
+                        const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
+                        const uint32_t idesc2 = p.idesc2;
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            umma_f16_lh(d_gram, a_lo + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc2, (xc | k4) != 0 ? 1u : 0u);
+                            umma_f16_lh(d_gram, a_lo + 2 * k4, a_hi_w, b_lo + (Cfg::B_PLANE >> 4) + 2 * k4, b_hi_w, idesc2, 1u);
+                            umma_f16_lh(d_gram, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc2, 1u);
+                        }
+                        umma_commit(bempty(bs));
+                        umma_commit(aempty(as));
+                        if (xc == xchunks - 1) umma_commit(xfull(xa));
+                    }
+                    __syncwarp();
+                    if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                     if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
                 }
             }
@@ -335,8 +387,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 mbar_arrive(mempty(mb));
             }
             if (split) {
-                const uint32_t xa = tcount & 1u;
-                mbar_wait(xfull(xa), (tcount >> 1) & 1u);
+                const bool xsingle = xchunks > 0;
+                const uint32_t xa = xsingle ? 0u : (tcount & 1u);
+                mbar_wait(xfull(xa), xsingle ? (tcount & 1u) : ((tcount >> 1) & 1u));
                 tc_fence_after();
 #pragma unroll
                 for (int c0 = 0; c0 < N_TILE; c0 += 32) {
@@ -345,6 +398,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+                }
+                if (xsingle) {
+                    // fused Gram term: acc (true units, alpha == 1 for data-gradients) += alpha2[frame] * (D * F)
+                    const int frx = (tile % tiles_m) / (p.tiles_x * p.tiles_y);
+                    const float a2 = __ldg(p.alpha2_dev + frx);
+#pragma unroll
+                    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(lane_base + (uint32_t)(3 * N_TILE) + c0, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c0 + j] = fmaf(a2, __uint_as_float(r[j]), acc[c0 + j]);
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(xempty(xa));

@@ -43,6 +43,9 @@ struct ConvParams {
     int passes;          // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi only
     int promote;         // k-steps (of 64 channels) per main accumulation chain, >= 1
     int b_frame;         // 1: third B coordinate is the frame (per-frame B, Gram backward), 0: the tap
+    int extra_chunks;      // conv_halo: fused Gram-backward k-steps appended to the convolution (0 = none)
+    uint32_t idesc2;       // instruction descriptor of those k-steps (fp16 features x fp16 D matrix)
+    const float* alpha2_dev;   // [NB] multiplier of the fused Gram accumulator
     int use_tma_store;     // conv_halo, CONV_FWD: the fp16 planes leave through shared memory + TMA store (tmO_hi / tmO_lo)
     int dbg_flags;         // timing experiments only: 2 = skip the A loads, 4 = skip the B loads (results are then garbage)
     long long* dbg_times;  // optional [gridDim.x][8] clock64 stamps of the kernel phases (IST_B200_DBG_TIMES=1)

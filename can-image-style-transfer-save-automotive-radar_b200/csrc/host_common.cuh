@@ -200,9 +200,18 @@ inline int launch_conv_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
     IST_CUDA(cudaGetLastError());
     return IST_OK;
 }
+// Gram backward fused into a data-gradient launch (conv_halo only): `chunks` extra k-steps A = feature planes (halo-box maps,
+// fp16), B = D matrix planes (fp16, [frame][C][C], scaled by 2^e), accumulated in their own tensor-memory accumulator and added
+// to the data-gradient as alpha[frame] * (D * F) in the epilogue.
+struct GramFuse {
+    const CUtensorMap *f_hi, *f_lo, *d_hi, *d_lo;
+    int chunks;
+    const float* alpha;     // [NB] device multipliers (gram_dmat_kernel's alpha_out)
+};
 template <int N_TILE>
 inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-                         const CUtensorMap& b_lo, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const ConvParams& p) {
+                         const CUtensorMap& b_lo, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const CUtensorMap& f_hi,
+                         const CUtensorMap& f_lo, const CUtensorMap& d_hi, const CUtensorMap& d_lo, const ConvParams& p) {
     static bool attr_done = false;
     if (!attr_done) {
         IST_CUDA(cudaFuncSetAttribute(conv_halo_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -214,7 +223,7 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
     const double px = (double)p.NB * p.H * p.W;
     const int planes = p.passes == 3 ? 2 : 1;
     launch_pre(p.taps == 9 ? (p.mode == CONV_FWD ? "conv_halo_fwd" : "conv_halo_dgrad") : "conv_halo_gram_bwd",
-               2.0 * px * p.Cout * p.Cin * p.taps,
+               2.0 * px * p.Cout * (p.Cin * p.taps + 64.0 * p.extra_chunks),
                planes * 2.0 * (px * p.Cin + (double)p.taps * p.Cin * p.Cout) + px * p.Cout * 4.0, st);
     static int dbg_on = -1;
     if (dbg_on < 0) { const char* e = getenv("IST_B200_DBG_TIMES"); dbg_on = (e != nullptr && atoi(e) == 1) ? 1 : 0; }
@@ -226,7 +235,7 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
         IST_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(long long) * 8 * 1024, st));
         ConvParams q = p;
         q.dbg_times = dbuf;
-        conv_halo_kernel<N_TILE><<<grid, 224, HaloCfg<N_TILE>::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, q);
+        conv_halo_kernel<N_TILE><<<grid, 224, HaloCfg<N_TILE>::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, q);
         IST_CUDA(cudaStreamSynchronize(st));
         std::vector<long long> h(8 * (size_t)grid);
         IST_CUDA(cudaMemcpy(h.data(), dbuf, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost));
@@ -239,7 +248,7 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
         launch_post(st);
         return IST_OK;
     }
-    conv_halo_kernel<N_TILE><<<grid, 224, HaloCfg<N_TILE>::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, p);
+    conv_halo_kernel<N_TILE><<<grid, 224, HaloCfg<N_TILE>::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, p);
     launch_post(st);
     IST_CUDA(cudaGetLastError());
     return IST_OK;
@@ -257,9 +266,13 @@ inline int promote_steps() {
 // Fills the tiling fields of p (NB,H,W,Cin,Cout,taps,passes,mode and epilogue pointers must be set) and launches.
 // o_hi / o_lo: optional tensor maps (map_act(..., taps = 1)) of the output planes; with them the conv_halo forward epilogue
 // leaves through shared memory + TMA store.
+// fmt: operand format of the k-steps, 0 = fp16 x fp16, 1 = bf16 x bf16 (mixing the two in one MMA is an illegal instruction on sm_100a)
+inline uint32_t conv_idesc(int fmt, int nt) {
+    return umma_idesc_f16(fmt == 1 ? UMMA_FMT_BF16 : UMMA_FMT_F16, 128, (uint32_t)nt, 0, 0);
+}
 inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-                       const CUtensorMap& b_lo, ConvParams p, bool bf16, const CUtensorMap* o_hi = nullptr,
-                       const CUtensorMap* o_lo = nullptr) {
+                       const CUtensorMap& b_lo, ConvParams p, int fmt, const CUtensorMap* o_hi = nullptr,
+                       const CUtensorMap* o_lo = nullptr, const GramFuse* gf = nullptr) {
     if (p.Cin % 64 != 0 || p.Cout % 64 != 0) return fail(IST_ERR_ARG, "conv_igemm needs Cin, Cout %% 64 == 0 (got %d, %d)", p.Cin, p.Cout);
     pick_tile(p.W, &p.TW, &p.TH);
     p.tiles_x = (p.W + p.TW - 1) / p.TW;
@@ -267,13 +280,27 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
     const int nt = conv_n_tile(p.Cout);
     p.tiles_n = p.Cout / nt;
     if (p.promote < 1) p.promote = promote_steps();
-    p.idesc = umma_idesc_f16(bf16 ? UMMA_FMT_BF16 : UMMA_FMT_F16, 128, nt, 0, 0);
+    p.idesc = conv_idesc(fmt, nt);
+    p.idesc2 = conv_idesc(0, nt);
+    p.extra_chunks = 0;
+    if (gf != nullptr && !conv_impl_halo()) return fail(IST_ERR_STATE, "the fused Gram backward needs the conv_halo kernel");
     if (conv_impl_halo()) {
+        if (gf != nullptr) {
+            if (p.taps != 9) return fail(IST_ERR_ARG, "fused Gram backward rides on a 3x3 data-gradient launch");
+            if (p.passes != 3) return fail(IST_ERR_ARG, "fused Gram backward needs the 3-pass split");
+            p.extra_chunks = gf->chunks;
+            p.alpha2_dev = gf->alpha;
+        }
         p.dbg_flags = halo_dbg_flags();
         p.use_tma_store = (p.out_f32 == nullptr && o_hi != nullptr && o_lo != nullptr) ? 1 : 0;
         const CUtensorMap& oh = p.use_tma_store ? *o_hi : a_hi;
         const CUtensorMap& ol = p.use_tma_store ? *o_lo : a_lo;
-        return nt == 128 ? launch_halo_t<128>(st, a_hi, a_lo, b_hi, b_lo, oh, ol, p) : launch_halo_t<64>(st, a_hi, a_lo, b_hi, b_lo, oh, ol, p);
+        const CUtensorMap& fh = gf != nullptr ? *gf->f_hi : a_hi;
+        const CUtensorMap& fl = gf != nullptr ? *gf->f_lo : a_lo;
+        const CUtensorMap& dh = gf != nullptr ? *gf->d_hi : b_hi;
+        const CUtensorMap& dl = gf != nullptr ? *gf->d_lo : b_lo;
+        return nt == 128 ? launch_halo_t<128>(st, a_hi, a_lo, b_hi, b_lo, oh, ol, fh, fl, dh, dl, p)
+                         : launch_halo_t<64>(st, a_hi, a_lo, b_hi, b_lo, oh, ol, fh, fl, dh, dl, p);
     }
     return nt == 128 ? launch_conv_t<128>(st, a_hi, a_lo, b_hi, b_lo, p) : launch_conv_t<64>(st, a_hi, a_lo, b_hi, b_lo, p);
 }

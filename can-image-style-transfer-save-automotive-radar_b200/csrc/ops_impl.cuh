@@ -82,7 +82,7 @@ int ist_op_conv3x3_relu_fwd(const float* x, const float* w, const float* b, floa
         memset(&p, 0, sizeof(p));
         p.NB = NB; p.H = H; p.W = W; p.Cin = cin; p.Cout = cout; p.taps = 9; p.passes = 3; p.mode = CONV_FWD;
         p.alpha = 1.f / (kS * ws); p.bias = b; p.out_scale = kS; p.out_hi = oh; p.out_lo = ol;
-        IST_TRY(launch_conv(st, a_hi, a_lo, b_hi, b_lo, p, false, &o_hi, &o_lo));
+        IST_TRY(launch_conv(st, a_hi, a_lo, b_hi, b_lo, p, 0, &o_hi, &o_lo));
     }
     IST_TRY(from_planes(st, oh, ol, y, NB, cout, HW, 1.f / kS, false));
     return IST_OK;
@@ -118,7 +118,7 @@ int ist_op_conv3x3_dgrad(const float* dy, const float* w, float* dx, int NB, int
     memset(&p, 0, sizeof(p));
     p.NB = NB; p.H = H; p.W = W; p.Cin = cout; p.Cout = cin; p.taps = 9; p.passes = passes == 1 ? 1 : 3; p.mode = CONV_GRAD;
     p.alpha = 1.f; p.out_f32 = o32;
-    IST_TRY(launch_conv(st, a_hi, a_lo, b_hi, b_lo, p, true));
+    IST_TRY(launch_conv(st, a_hi, a_lo, b_hi, b_lo, p, 1));
     nhwc_to_nchw_f32_kernel<<<ew_grid((size_t)NB * HW * cin, 256), 256, 0, st>>>(o32, dx, NB, cin, HW);
     IST_CUDA(cudaGetLastError());
     return IST_OK;
@@ -256,7 +256,7 @@ static int gram_common(const float* x, const float* target, float weight, float*
     memset(&p, 0, sizeof(p));
     p.NB = NB; p.H = H; p.W = W; p.Cin = C; p.Cout = C; p.taps = 1; p.b_frame = 1; p.passes = 3; p.mode = CONV_GRAD;
     p.alpha = 1.f; p.alpha_dev = alpha; p.alpha_stride = 1; p.out_f32 = o32;
-    IST_TRY(launch_conv(st, a_hi, a_lo, b_hi, b_lo, p, false));
+    IST_TRY(launch_conv(st, a_hi, a_lo, b_hi, b_lo, p, 0));
     nhwc_to_nchw_f32_kernel<<<ew_grid((size_t)NB * HW * C, 256), 256, 0, st>>>(o32, dx, NB, C, HW);
     IST_CUDA(cudaGetLastError());
     return IST_OK;

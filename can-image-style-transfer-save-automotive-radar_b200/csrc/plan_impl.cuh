@@ -115,7 +115,7 @@ int run_forward(ist_plan* P, const float* x, int upto, cudaStream_t st) {
                 p.bias = L.bias;
                 p.out_scale = kActScale;
                 p.out_hi = L.out.hi; p.out_lo = L.out.lo;
-                IST_TRY(launch_conv(st, L.mA_hi, L.mA_lo, L.mBf_hi, L.mBf_lo, p, false, &L.mO_hi, &L.mO_lo));
+                IST_TRY(launch_conv(st, L.mA_hi, L.mA_lo, L.mBf_hi, L.mBf_lo, p, 0, &L.mO_hi, &L.mO_lo));
             }
         } else {
             const Layer& I = P->layers[l - 1];
@@ -194,11 +194,11 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         *coef = (float)(2.0 * L.content_w / ((double)L.C * L.H * L.W * kActScale));
     };
     // dgrad of conv `cj` (layer index) into the gradient of its input tensor
-    auto dgrad = [&](const Layer& Cj, ConvParams p, const Layer* dst) -> int {
+    auto dgrad = [&](const Layer& Cj, ConvParams p, const Layer* dst, const GramFuse* gf = nullptr) -> int {
         p.NB = NB; p.H = Cj.H; p.W = Cj.W; p.Cin = Cj.cout; p.Cout = Cj.cin; p.taps = 9;
         p.passes = P->passes_bwd; p.mode = CONV_GRAD; p.alpha = 1.f;
-        return launch_conv(st, Cj.mG_hi, Cj.mG_lo, Cj.mBd_hi, Cj.mBd_lo, p, true, dst != nullptr ? &dst->mGo_hi : nullptr,
-                           dst != nullptr ? &dst->mGo_lo : nullptr);
+        return launch_conv(st, Cj.mG_hi, Cj.mG_lo, Cj.mBd_hi, Cj.mBd_lo, p, 1, dst != nullptr ? &dst->mGo_hi : nullptr,
+                           dst != nullptr ? &dst->mGo_lo : nullptr, gf);
     };
     auto gram_bwd = [&](Layer& L, const float* addend, bool content) -> int {
         ConvParams p;
@@ -210,7 +210,7 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         if (content) set_content(L, &p.f_hi, &p.f_lo, &p.t_hi, &p.t_lo, &p.content_coef);
         p.mask_hi = L.out.hi;
         p.out_hi = L.dY.hi; p.out_lo = L.dY.lo;
-        return launch_conv(st, L.mFeat_hi, L.mFeat_lo, L.mD_hi, L.mD_lo, p, false, &L.mGo_hi, &L.mGo_lo);
+        return launch_conv(st, L.mFeat_hi, L.mFeat_lo, L.mD_hi, L.mD_lo, p, 0, &L.mGo_hi, &L.mGo_lo);
     };
     auto route = [&](Layer& L, const float* g_pool, const float* addend, bool content, bool to_f32, float* f32_out) -> int {
         RouteParams r;
@@ -245,7 +245,14 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
             memset(&p, 0, sizeof(p));
             p.addend = ext(L);
             if (content) set_content(L, &p.f_hi, &p.f_lo, &p.t_hi, &p.t_lo, &p.content_coef);
-            if (style) {
+            if (style && conv_impl_halo() && P->passes_bwd == 3) {
+                // style seed D * F_l accumulated inside the data-gradient launch of conv l+1: F_l's halo-box maps are the
+                // forward A maps of conv l+1
+                GramFuse gf = {&Cn.mA_hi, &Cn.mA_lo, &L.mD_hi, &L.mD_lo, L.C / 64, L.alpha};
+                p.mask_hi = L.out.hi;
+                p.out_hi = L.dY.hi; p.out_lo = L.dY.lo;
+                IST_TRY(dgrad(Cn, p, &L, &gf));
+            } else if (style) {
                 p.out_f32 = P->fbuf[1];
                 IST_TRY(dgrad(Cn, p, nullptr));
                 IST_TRY(gram_bwd(L, P->fbuf[1], false));

@@ -182,6 +182,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
 enum : uint32_t { UMMA_FMT_F16 = 0, UMMA_FMT_BF16 = 1 };
 
 // Instruction descriptor for kind::f16 with fp32 accumulation.
+__host__ __device__ constexpr uint32_t umma_idesc_f16_ab(uint32_t a_fmt, uint32_t b_fmt, uint32_t M, uint32_t N,
+                                                         uint32_t a_mn_major, uint32_t b_mn_major) {
+    return (1u << 4)                 // [4,6)   D format: 1 = F32
+           | (a_fmt << 7)            // [7,10)  A format
+           | (b_fmt << 10)           // [10,13) B format
+           | (a_mn_major << 15)      // [15]    A major: 0 = K, 1 = MN
+           | (b_mn_major << 16)      // [16]    B major
+           | ((N >> 3) << 17)        // [17,23) N >> 3
+           | ((M >> 4) << 24);       // [24,29) M >> 4
+}
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t fmt, uint32_t M, uint32_t N, uint32_t a_mn_major,
                                                       uint32_t b_mn_major) {
     return (1u << 4)                 // [4,6)   D format: 1 = F32
