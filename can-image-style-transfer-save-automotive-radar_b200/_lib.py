@@ -83,6 +83,7 @@ SIGNATURES = {
     "ist_plan_backward": (ctypes.c_int, [_vp, ctypes.c_int, _c_int_p, ctypes.POINTER(_vp), _vp, _vp]),
     "ist_lbfgs_create": (ctypes.c_int, [ctypes.POINTER(_vp), _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_double]),
     "ist_lbfgs_destroy": (ctypes.c_int, [_vp]),
+    "ist_lbfgs_reset": (ctypes.c_int, [_vp, _vp]),
     "ist_lbfgs_step": (ctypes.c_int, [_vp, _vp, _c_int_p, _c_float_p, _vp]),
     "ist_lbfgs_last_losses": (ctypes.c_int, [_vp, _c_float_p]),
     "ist_op_conv3x3_relu_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp] + [ctypes.c_int] * 6 + [_vp]),

@@ -520,7 +520,7 @@ struct GramLayer {
     float weight;           // loss weight (STYLE_WEIGHTS[k], defaults.py:68)
     float bwd_coef;         // 2*w / (C^2 * H*W * s_act)
 };
-constexpr int GRAM_FIN_BLOCKS = 64;
+constexpr int GRAM_FIN_BLOCKS = 128;
 struct GramFinalizeParams {
     GramLayer L[8];
     int n_layers, NB, loss_stride;

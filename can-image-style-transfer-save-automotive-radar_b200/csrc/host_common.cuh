@@ -328,7 +328,7 @@ inline void gram_split_plan(int NB, int HW, int C, int* splits, int* chunks_per_
     int want = (num_sms() + tri * NB - 1) / (tri * NB);     // ~one CTA per SM; accuracy does not depend on the split (register promotion)
     if (want < 1) want = 1;
     if (want > total_chunks) want = total_chunks;
-    if (want > 64) want = 64;
+    if (want > 160) want = 160;
     const int cps = (total_chunks + want - 1) / want;
     *chunks_per_split = cps;
     *splits = (total_chunks + cps - 1) / cps;

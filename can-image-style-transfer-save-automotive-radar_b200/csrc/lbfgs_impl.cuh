@@ -461,7 +461,7 @@ struct ist_lbfgs {
     int n_losses = 0;
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
-    float* graph_x = nullptr;
+    float* x_own = nullptr;          // optimiser-owned copy of the image: the graph is captured once on it, callers' x is copied in / out
     bool use_graph = true;
     unsigned long long graph_kernels = 0;
     std::vector<ist::LbFrame> host_frames;
@@ -516,6 +516,7 @@ int ist_lbfgs_create(ist_lbfgs** out, ist_plan* plan, int history_size, int max_
     const size_t vn = (size_t)P.NB * P.n;
     int rc = IST_OK;
     if (rc == IST_OK) rc = O->mem.alloc(&O->g, vn);
+    if (rc == IST_OK) rc = O->mem.alloc(&O->x_own, vn);
     if (rc == IST_OK) rc = O->mem.alloc(&O->losses, (size_t)P.NB * P.loss_stride);
     if (rc == IST_OK) rc = O->mem.alloc(&P.prev_g, vn);
     if (rc == IST_OK) rc = O->mem.alloc(&P.d, vn);
@@ -553,19 +554,30 @@ int ist_lbfgs_destroy(ist_lbfgs* O) {
     return IST_OK;
 }
 
+int ist_lbfgs_reset(ist_lbfgs* O, void* stream) {
+    using namespace ist;
+    if (O == nullptr) return fail(IST_ERR_ARG, "ist_lbfgs_reset: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const LbParams& P = O->P;
+    // a fresh torch.optim.LBFGS([x]) (utils.py:24): empty state; the history buffers need no clearing (hist_len = 0)
+    IST_CUDA(cudaMemsetAsync(P.frames, 0, sizeof(LbFrame) * P.NB, st));
+    IST_CUDA(cudaMemsetAsync(P.dmax_part, 0, sizeof(float) * P.NB * P.nblk, st));
+    return IST_OK;
+}
+
 int ist_lbfgs_step(ist_lbfgs* O, float* x_dev, int* evals_out, float* loss_out, void* stream) {
     using namespace ist;
     if (O == nullptr || x_dev == nullptr) return fail(IST_ERR_ARG, "ist_lbfgs_step: null argument");
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t xbytes = sizeof(float) * (size_t)O->P.NB * O->P.n;
     if (O->use_graph) {
-        if (O->graph_exec == nullptr || O->graph_x != x_dev) {
-            if (O->graph_exec != nullptr) { cudaGraphExecDestroy(O->graph_exec); O->graph_exec = nullptr; }
+        if (O->graph_exec == nullptr) {
             if (O->cap_stream == nullptr) IST_CUDA(cudaStreamCreateWithFlags(&O->cap_stream, cudaStreamNonBlocking));
             IST_CUDA(cudaStreamSynchronize(st));
             IST_CUDA(cudaStreamBeginCapture(O->cap_stream, cudaStreamCaptureModeThreadLocal));
             book().capturing = true;
             book().captured = 0;
-            int rc = lbfgs_enqueue_step(O, x_dev, O->cap_stream);
+            int rc = lbfgs_enqueue_step(O, O->x_own, O->cap_stream);
             book().capturing = false;
             O->graph_kernels = book().captured;
             cudaGraph_t graph = nullptr;
@@ -575,9 +587,10 @@ int ist_lbfgs_step(ist_lbfgs* O, float* x_dev, int* evals_out, float* loss_out, 
             e = cudaGraphInstantiate(&O->graph_exec, graph, 0);
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) return fail(IST_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
-            O->graph_x = x_dev;
         }
+        IST_CUDA(cudaMemcpyAsync(O->x_own, x_dev, xbytes, cudaMemcpyDeviceToDevice, st));
         IST_CUDA(cudaGraphLaunch(O->graph_exec, st));
+        IST_CUDA(cudaMemcpyAsync(x_dev, O->x_own, xbytes, cudaMemcpyDeviceToDevice, st));
         book().launches += O->graph_kernels;
     } else {
         IST_TRY(lbfgs_enqueue_step(O, x_dev, st));

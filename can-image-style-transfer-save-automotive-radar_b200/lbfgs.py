@@ -19,6 +19,10 @@ class DeviceLBFGS:
         self.h = h
         self.n_losses = plan.n_style + plan.n_content
 
+    def reset(self):
+        """Forget all optimiser state (equivalent to constructing a new optim.LBFGS([x])); keeps buffers and the captured graph."""
+        _lib.check(self.lib.ist_lbfgs_reset(self.h, _lib.stream_ptr()))
+
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
             self.lib.ist_lbfgs_destroy(self.h)

@@ -92,19 +92,25 @@ def optimize(model, content_image, style_image, optimized_image, cfg, max_iterat
     for k in range(len(content_keys)):
         plan.capture_content_target(k)
 
-    # create optimizer (utils.py:24) and run (utils.py:28-43)
-    optimizer = DeviceLBFGS(plan)
+    # create optimizer (utils.py:24) and run (utils.py:28-43). The device optimiser (history buffers + the captured CUDA graph
+    # of one step) is kept on the plan and reset to the state of a fresh optim.LBFGS([x]) for every call.
+    optimizer = getattr(plan, "_lbfgs", None)
+    loss_key = (tuple(style_keys), tuple(float(v) for v in style_w), tuple(content_keys), tuple(float(v) for v in content_w))
+    if optimizer is None or optimizer.h is None or getattr(plan, "_lbfgs_key", None) != loss_key:
+        if optimizer is not None:
+            optimizer.close()                 # the captured graph bakes in the loss configuration
+        optimizer = DeviceLBFGS(plan)
+        plan._lbfgs = optimizer
+        plan._lbfgs_key = loss_key
+    optimizer.reset()
     iterations = [0]
-    try:
-        while iterations[0] < max_iterations:
-            evals, _ = optimizer.step(x)
-            iterations[0] += evals
-            if evals == 0:
-                raise _lib.IstError("L-BFGS made no closure evaluation")
-        model.last_losses = optimizer.last_losses()
-        model.last_evals = iterations[0]
-    finally:
-        optimizer.close()
+    while iterations[0] < max_iterations:
+        evals, _ = optimizer.step(x)
+        iterations[0] += evals
+        if evals == 0:
+            raise _lib.IstError("L-BFGS made no closure evaluation")
+    model.last_losses = optimizer.last_losses()
+    model.last_evals = iterations[0]
     return optimized_image
 
 

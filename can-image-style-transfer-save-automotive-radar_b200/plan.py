@@ -47,6 +47,10 @@ class Plan:
         self.device = torch.device("cuda", torch.cuda.current_device())
 
     def close(self):
+        opt = getattr(self, "_lbfgs", None)
+        if opt is not None:
+            opt.close()
+            self._lbfgs = None
         if getattr(self, "h", None) is not None and self.h.value:
             self.lib.ist_plan_destroy(self.h)
             self.h = None

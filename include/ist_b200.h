@@ -101,6 +101,9 @@ typedef struct ist_lbfgs ist_lbfgs;
 int ist_lbfgs_create(ist_lbfgs** out, ist_plan* plan, int history_size, int max_iter, int max_eval, float lr,
                      double tolerance_grad, double tolerance_change);
 int ist_lbfgs_destroy(ist_lbfgs* opt);
+/* back to the state of a freshly constructed optimiser (a new `optim.LBFGS([x])` per frame, IST/model/engine/utils.py:24)
+ * without re-allocating the history or re-capturing the CUDA graph */
+int ist_lbfgs_reset(ist_lbfgs* opt, void* stream);
 /* one optimizer.step(closure) on x (updated in place); evals_out += closure evaluations performed;
  * loss_out (host) = loss of the first closure call of this step, as LBFGS.step returns it. Synchronises once. */
 int ist_lbfgs_step(ist_lbfgs* opt, float* x_dev, int* evals_out, float* loss_out, void* stream);
