@@ -226,6 +226,8 @@ def run_ours(args):
     value = evals / (ms * 1e-3)
 
     # ---- end-to-end arm (host buffers) ------------------------------------------------------------------------------------
+    if world > 1:        # communicator set-up (lazy in NCCL) is not part of a frame's cost: run the gather once untimed
+        gather_frames(torch.zeros(args.steps, 3, SIZE, SIZE, device=dev), world * args.steps, rank, world)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
