@@ -362,7 +362,7 @@ inline int launch_gram(cudaStream_t st, const CUtensorMap& m_hi, const CUtensorM
 
 inline int ew_grid(size_t work_items, int block) {
     size_t g = (work_items + block - 1) / block;
-    const size_t cap = (size_t)num_sms() * 16;
+    const size_t cap = (size_t)num_sms() * 32;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;

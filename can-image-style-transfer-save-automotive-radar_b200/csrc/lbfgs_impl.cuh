@@ -53,6 +53,7 @@ struct LbParams {
     float* S;                     // [m][NB][n]
     float* Y;                     // [m][NB][n]
     double* part;                 // [NB][nblk][LB_PART]
+    double* tot;                  // [NB][LB_PART] fixed-order sums (max for the |g| entry) of `part`
     float* dmax_part;             // [NB][nblk]
     double* SY;                   // [NB][LB_MAXH][LB_MAXH]  s_i.y_j by physical slot
     double* YY;                   // [NB][LB_MAXH][LB_MAXH]
@@ -188,12 +189,44 @@ lbfgs_dots_kernel(const LbParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// pass 2: scalar logic of one iteration of LBFGS.step for one frame (one CTA of 128 threads).
+// pass 1b: fixed-order reduction of the per-CTA partials, one warp per output (grid (ceil(LB_PART / 8), NB), 256 threads):
+// lane l sums entries l, l + 32, ... in order, then a shuffle tree — the same order on every run.
 // ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lbfgs_reduce_kernel(const LbParams P) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // clears the "iteration computed" marker and remembers the step size of the direction that led to the gradient being
+        // processed (the solve replaces F.t with the step size of the new direction)
+        LbFrame& F = P.frames[b];
+        F.cg = 0.f;
+        F.t_prev_f = (float)F.t;
+    }
+    if (i >= LB_PART) return;
+    const double* p = P.part + (size_t)b * P.nblk * LB_PART + i;
+    const bool is_max = (i == 5 * LB_MAXH + 6);
+    double s = 0.0;
+    for (int k = lane; k < P.nblk; k += 32) {
+        const double v = p[(size_t)k * LB_PART];
+        s = is_max ? fmax(s, v) : s + v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double t = __shfl_xor_sync(0xffffffffu, s, o);
+        s = is_max ? fmax(s, t) : s + t;
+    }
+    if (lane == 0) P.tot[(size_t)b * LB_PART + i] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pass 2: scalar logic of one iteration of LBFGS.step for one frame (one CTA of LB_SOLVE_THREADS threads).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int LB_SOLVE_THREADS = 512;
 inline __host__ __device__ int lb_ld(int m) { return m + 1; }   // padded leading dimension of the smem matrices
 inline size_t lb_solve_smem(int m) { return 2 * (size_t)m * lb_ld(m) * sizeof(double); }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(LB_SOLVE_THREADS)
 lbfgs_solve_kernel(const LbParams P) {
     extern __shared__ double sm[];
     const int LB_LD = lb_ld(P.m);
@@ -201,24 +234,14 @@ lbfgs_solve_kernel(const LbParams P) {
     double* YYs = sm + (size_t)P.m * LB_LD;    // [m][LB_LD]
     __shared__ double tot[LB_PART];
     __shared__ double al_s[LB_MAXH], c_s[LB_MAXH], sg_s[LB_MAXH], yg_s[LB_MAXH];
-    __shared__ double red[128];
+    __shared__ double red[LB_MAXH];
     __shared__ int sh_go, sh_h;
     const int b = blockIdx.x, tid = threadIdx.x, m = P.m;
     LbFrame& F = P.frames[b];
     double* SYg = P.SY + (size_t)b * LB_MAXH * LB_MAXH;
     double* YYg = P.YY + (size_t)b * LB_MAXH * LB_MAXH;
 
-    // fixed-order reduction of the per-CTA partials
-    for (int i = tid; i < LB_PART; i += blockDim.x) {
-        double s = 0.0;
-        const double* p = P.part + (size_t)b * P.nblk * LB_PART + i;
-        if (i == 5 * LB_MAXH + 6) {
-            for (int k = 0; k < P.nblk; ++k) s = fmax(s, p[(size_t)k * LB_PART]);
-        } else {
-            for (int k = 0; k < P.nblk; ++k) s += p[(size_t)k * LB_PART];
-        }
-        tot[i] = s;
-    }
+    for (int i = tid; i < LB_PART; i += blockDim.x) tot[i] = P.tot[(size_t)b * LB_PART + i];
     __syncthreads();
     const double* st = &tot[5 * LB_MAXH];
     const double ys = st[0], yy = st[1], sg_new = st[2], yg_new = st[3], gg = st[4], g1 = st[5], gmax = st[6];
@@ -302,37 +325,47 @@ lbfgs_solve_kernel(const LbParams P) {
     }
     __syncthreads();
 
-    // first loop (lbfgs.py:431-436), newest to oldest: al_i = ro_i * s_i.q with q = -g - sum_{j>i} al_j y_j
+    // The two sequential loops run on the first 4 warps only (h <= 100 < 128), synchronised with a named barrier: a barrier
+    // over 4 warps is several times cheaper than one over the 16 warps that loaded the matrices.
     const double H = F.H_diag;
-    double u = 0.0;                              // thread k: sum_{j processed} al_j * (s_k . y_j)
-    for (int i = h - 1; i >= 0; --i) {
-        if (tid == i) al_s[i] = F.ro[phys(i)] * (-sg_s[i] - u);
-        __syncthreads();
-        if (tid < i) u += al_s[i] * SYs[tid * LB_LD + i];
-    }
-    __syncthreads();
-    // r = H*q: y_k . r before the second loop
-    double v = 0.0, w = 0.0;
-    if (tid < h) {
-        double acc = -yg_s[tid];
-        for (int j = 0; j < h; ++j) acc -= al_s[j] * YYs[tid * LB_LD + j];
-        v = H * acc;
-    }
-    // second loop (lbfgs.py:440-443), oldest to newest: be_i = ro_i * y_i.r ; r += (al_i - be_i) s_i
-    for (int i = 0; i < h; ++i) {
-        if (tid == i) c_s[i] = al_s[i] - F.ro[phys(i)] * (v + w);
-        __syncthreads();
-        if (tid > i && tid < h) w += c_s[i] * SYs[i * LB_LD + tid];
+    if (tid < 128) {
+        // first loop (lbfgs.py:431-436), newest to oldest: al_i = ro_i * s_i.q with q = -g - sum_{j>i} al_j y_j
+        const double ro_t = tid < h ? F.ro[phys(tid)] : 0.0;
+        double u = 0.0;                              // thread k: sum_{j processed} al_j * (s_k . y_j)
+        for (int i = h - 1; i >= 0; --i) {
+            if (tid == i) al_s[i] = ro_t * (-sg_s[i] - u);
+            named_bar_sync(1, 128);
+            if (tid < i) u += al_s[i] * SYs[tid * LB_LD + i];
+        }
+        named_bar_sync(1, 128);
+        // r = H*q: y_k . r before the second loop
+        double v = 0.0, w = 0.0;
+        if (tid < h) {
+            double acc = -yg_s[tid];
+            for (int j = 0; j < h; ++j) acc -= al_s[j] * YYs[tid * LB_LD + j];
+            v = H * acc;
+        }
+        // second loop (lbfgs.py:440-443), oldest to newest: be_i = ro_i * y_i.r ; r += (al_i - be_i) s_i
+        for (int i = 0; i < h; ++i) {
+            if (tid == i) c_s[i] = al_s[i] - ro_t * (v + w);
+            named_bar_sync(1, 128);
+            if (tid > i && tid < h) w += c_s[i] * SYs[i * LB_LD + tid];
+        }
     }
     __syncthreads();
     // gtd = g.d with d = -H g - sum H al_j y_j + sum c_j s_j
-    double part = 0.0;
-    if (tid < h) part = -H * al_s[tid] * yg_s[tid] + c_s[tid] * sg_s[tid];
-    red[tid] = part;
+    if (tid < LB_MAXH) red[tid] = (tid < h) ? (-H * al_s[tid] * yg_s[tid] + c_s[tid] * sg_s[tid]) : 0.0;
+    // coefficients of the update pass: an accepted pair is always the newest one, i.e. logical index h - 1
+    const int nread = accepted ? h - 1 : h;
+    if (tid < nread) {
+        F.read_slot[tid] = phys(tid);
+        F.read_cy[tid] = (float)(-H * al_s[tid]);
+        F.read_cs[tid] = (float)c_s[tid];
+    }
     __syncthreads();
     if (tid == 0) {
         double gtd = -H * gg;
-        for (int k = 0; k < 128; ++k) gtd += red[k];
+        for (int k = 0; k < h; ++k) gtd += red[k];
         F.gtd = gtd;
         F.prev_loss = F.loss;                                            // lbfgs.py:449
         double t;
@@ -345,14 +378,8 @@ lbfgs_solve_kernel(const LbParams P) {
         F.t = t;
         F.t_f = (float)t;
         F.cg = (float)(-H);
-        int nread = 0;
-        F.cy_new = 0.f; F.cs_new = 0.f;
-        for (int i = 0; i < h; ++i) {
-            const int p = phys(i);
-            const float cy = (float)(-H * al_s[i]), cs = (float)c_s[i];
-            if (accepted && p == new_slot) { F.cy_new = cy; F.cs_new = cs; }
-            else { F.read_slot[nread] = p; F.read_cy[nread] = cy; F.read_cs[nread] = cs; ++nread; }
-        }
+        F.cy_new = accepted ? (float)(-H * al_s[h - 1]) : 0.f;
+        F.cs_new = accepted ? (float)c_s[h - 1] : 0.f;
         F.nread = nread;
         if (gtd > -P.tol_change) { F.active = 0; F.apply = 0; }          // lbfgs.py:462-464 (break before the update)
         else F.apply = 1;
@@ -399,7 +426,7 @@ lbfgs_update_kernel(const LbParams P) {
 #pragma unroll
                 for (int e = 0; e < 16; ++e) { yv[e] = gv[e] - yv[e]; }
                 if (accepted) {
-                    // s_new = t_prev * d_old (lbfgs.py:404): t_prev is the step size saved by lbfgs_prep_kernel before the
+                    // s_new = t_prev * d_old (lbfgs.py:404): t_prev is the step size saved by lbfgs_reduce_kernel before the
                     // solve replaced F.t with the step size of the new direction
                     const float tp = F.t_prev_f;
 #pragma unroll
@@ -441,15 +468,6 @@ lbfgs_update_kernel(const LbParams P) {
     }
 }
 
-// clears the "iteration computed" marker and remembers the previous step size for the update pass
-__global__ void lbfgs_prep_kernel(const LbParams P) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= P.NB) return;
-    LbFrame& F = P.frames[b];
-    F.cg = 0.f;
-    F.t_prev_f = (float)F.t;     // step size of the direction that led to the gradient being processed
-}
-
 }  // namespace ist
 
 struct ist_lbfgs {
@@ -476,9 +494,9 @@ inline int lbfgs_enqueue_step(ist_lbfgs* O, float* x, cudaStream_t st) {
         IST_TRY(ist_plan_loss_and_grad(O->plan, x, O->g, O->losses, (void*)st));
         P.it = it;
         const double vb = 4.0 * P.NB * (double)P.n;
-        IST_EW("lbfgs_prep", 64.0, st, lbfgs_prep_kernel<<<(P.NB + 63) / 64, 64, 0, st>>>(P));
         IST_EW("lbfgs_dots", vb * (3 + 2.0 * P.m), st, lbfgs_dots_kernel<<<dim3(P.nblk, P.NB), 256, 0, st>>>(P));
-        IST_EW("lbfgs_solve", 16.0 * P.m * P.m, st, lbfgs_solve_kernel<<<P.NB, 128, lb_solve_smem(P.m), st>>>(P));
+        IST_EW("lbfgs_reduce", 8.0 * P.NB * P.nblk * LB_PART, st, lbfgs_reduce_kernel<<<dim3((LB_PART + 7) / 8, P.NB), 256, 0, st>>>(P));
+        IST_EW("lbfgs_solve", 16.0 * P.m * P.m, st, lbfgs_solve_kernel<<<P.NB, LB_SOLVE_THREADS, lb_solve_smem(P.m), st>>>(P));
         IST_EW("lbfgs_update", vb * (9 + 2.0 * P.m), st, lbfgs_update_kernel<<<dim3(P.nblk, P.NB), 256, 0, st>>>(P));
     }
     return IST_OK;
@@ -523,6 +541,7 @@ int ist_lbfgs_create(ist_lbfgs** out, ist_plan* plan, int history_size, int max_
     if (rc == IST_OK) rc = O->mem.alloc(&P.S, vn * P.m);
     if (rc == IST_OK) rc = O->mem.alloc(&P.Y, vn * P.m);
     if (rc == IST_OK) rc = O->mem.alloc(&P.part, (size_t)P.NB * P.nblk * LB_PART);
+    if (rc == IST_OK) rc = O->mem.alloc(&P.tot, (size_t)P.NB * LB_PART);
     if (rc == IST_OK) rc = O->mem.alloc(&P.dmax_part, (size_t)P.NB * P.nblk);
     if (rc == IST_OK) rc = O->mem.alloc(&P.SY, (size_t)P.NB * LB_MAXH * LB_MAXH);
     if (rc == IST_OK) rc = O->mem.alloc(&P.YY, (size_t)P.NB * LB_MAXH * LB_MAXH);

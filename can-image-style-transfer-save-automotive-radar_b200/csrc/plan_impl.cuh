@@ -70,6 +70,15 @@ struct ist_plan {
     float* losses = nullptr;       // [NB][kMaxLoss+1] device scratch
     int forwarded_upto = -1;
     int passes_fwd = 3, passes_bwd = 3;
+    // side stream for loss work that does not depend on the deepest layer (runs while the deepest conv, which has too few
+    // tiles to fill the GPU, is computed)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    ~ist_plan() {
+        if (ev_fork != nullptr) cudaEventDestroy(ev_fork);
+        if (ev_join != nullptr) cudaEventDestroy(ev_join);
+        if (side != nullptr) cudaStreamDestroy(side);
+    }
 };
 
 namespace {
@@ -93,8 +102,8 @@ int alloc_planes(DevMem& mem, Planes* p, size_t elems) {
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
-int run_forward(ist_plan* P, const float* x, int upto, cudaStream_t st) {
-    for (int l = 0; l <= upto; ++l) {
+int run_forward(ist_plan* P, const float* x, int upto, cudaStream_t st, int from = 0) {
+    for (int l = from; l <= upto; ++l) {
         Layer& L = P->layers[l];
         if (L.kind == IST_LAYER_CONV3X3_RELU) {
             if (!L.has_weights) return fail(IST_ERR_STATE, "conv layer %d has no weights (ist_plan_set_weights)", l);
@@ -296,18 +305,36 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
     return IST_OK;
 }
 
-int run_losses(ist_plan* P, float* losses_dev, cudaStream_t st) {
+// Partial sums of the losses whose layer index lies in [lo, hi]: Gram split-K partials of the style layers, squared-error
+// partials of the content layers.
+int run_loss_partials(ist_plan* P, int lo, int hi, cudaStream_t st) {
+    for (int k = 0; k < P->n_style; ++k) {
+        const int l = P->style_layers[k];
+        if (l < lo || l > hi) continue;
+        Layer& L = P->layers[l];
+        if (!L.target_set) return fail(IST_ERR_STATE, "style target %d not set", k);
+        IST_TRY(run_gram_partial(P, L, st));
+    }
+    for (int k = 0; k < P->n_content; ++k) {
+        const int l = P->content_layers[k];
+        if (l < lo || l > hi) continue;
+        Layer& L = P->layers[l];
+        if (!L.content_set) return fail(IST_ERR_STATE, "content target %d not captured", k);
+        const size_t n8 = (size_t)L.H * L.W * L.C / 8;
+        dim3 grid(kContentBlocks, P->NB);
+        IST_EW("content_partial", (double)L.out_elems * 8, st,
+               content_partial_kernel<<<grid, 256, 0, st>>>(L.out.hi, L.out.lo, L.T.hi, L.T.lo, n8, L.c_partial));
+    }
+    return IST_OK;
+}
+
+int run_loss_finalize(ist_plan* P, float* losses_dev, cudaStream_t st) {
     const int stride = P->n_style + P->n_content + 1;
     GramFinalizeParams gp;
     memset(&gp, 0, sizeof(gp));
     gp.NB = P->NB;
     gp.loss_stride = stride;
-    for (int k = 0; k < P->n_style; ++k) {
-        Layer& L = P->layers[P->style_layers[k]];
-        if (!L.target_set) return fail(IST_ERR_STATE, "style target %d not set", k);
-        IST_TRY(run_gram_partial(P, L, st));
-        fill_gram_layer(P, L, &gp.L[gp.n_layers++], nullptr, losses_dev);
-    }
+    for (int k = 0; k < P->n_style; ++k) fill_gram_layer(P, P->layers[P->style_layers[k]], &gp.L[gp.n_layers++], nullptr, losses_dev);
     if (gp.n_layers > 0) {
         dim3 grid(GRAM_FIN_BLOCKS, gp.n_layers, P->NB);
         double rb = 0, db = 0;
@@ -327,11 +354,6 @@ int run_losses(ist_plan* P, float* losses_dev, cudaStream_t st) {
     lt.c_blocks = kContentBlocks;
     for (int k = 0; k < P->n_content; ++k) {
         Layer& L = P->layers[P->content_layers[k]];
-        if (!L.content_set) return fail(IST_ERR_STATE, "content target %d not captured", k);
-        const size_t n8 = (size_t)L.H * L.W * L.C / 8;
-        dim3 grid(kContentBlocks, P->NB);
-        IST_EW("content_partial", (double)L.out_elems * 8, st,
-               content_partial_kernel<<<grid, 256, 0, st>>>(L.out.hi, L.out.lo, L.T.hi, L.T.lo, n8, L.c_partial));
         lt.c_partial[k] = L.c_partial;
         lt.c_slot[k] = P->n_style + k;
         lt.c_scale[k] = (float)((double)L.content_w / ((double)L.C * L.H * L.W * kActScale * kActScale));
@@ -467,6 +489,9 @@ int ist_plan_create(ist_plan** out, int n_layers, const ist_layer_desc* layers, 
         if (rc == IST_OK) rc = map_act(&L.mG_hi, L.dY.hi, batch, L.H, L.W, L.cout, 9);
         if (rc == IST_OK) rc = map_act(&L.mG_lo, L.dY.lo, batch, L.H, L.W, L.cout, 9);
     }
+    if (rc == IST_OK && cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking) != cudaSuccess) rc = fail(IST_ERR_CUDA, "cudaStreamCreate failed");
+    if (rc == IST_OK && cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming) != cudaSuccess) rc = fail(IST_ERR_CUDA, "cudaEventCreate failed");
+    if (rc == IST_OK && cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming) != cudaSuccess) rc = fail(IST_ERR_CUDA, "cudaEventCreate failed");
     if (rc != IST_OK) {
         delete P;
         return rc;
@@ -614,8 +639,24 @@ int ist_plan_loss_and_grad(ist_plan* P, const float* x_dev, float* grad_dev, flo
     if (deepest < 0) return fail(IST_ERR_STATE, "no loss configured (ist_plan_set_loss)");
     cudaStream_t st = (cudaStream_t)stream;
     for (Layer& L : P->layers) L.ext_active = false;
-    IST_TRY(run_forward(P, x_dev, deepest, st));
-    IST_TRY(run_losses(P, losses_dev, st));
+    static int overlap_env = -1;
+    if (overlap_env < 0) { const char* e = getenv("IST_B200_NO_OVERLAP"); overlap_env = (e != nullptr && atoi(e) == 1) ? 0 : 1; }
+    if (overlap_env && deepest >= 2 && P->side != nullptr) {
+        // everything up to the layer before the deepest one, then fork: the loss partials of the shallower layers run on the
+        // side stream while the deepest conv (few tiles) runs on the main stream
+        IST_TRY(run_forward(P, x_dev, deepest - 1, st));
+        IST_CUDA(cudaEventRecord(P->ev_fork, st));
+        IST_CUDA(cudaStreamWaitEvent(P->side, P->ev_fork, 0));
+        IST_TRY(run_loss_partials(P, 0, deepest - 1, P->side));
+        IST_CUDA(cudaEventRecord(P->ev_join, P->side));
+        IST_TRY(run_forward(P, x_dev, deepest, st, deepest));
+        IST_TRY(run_loss_partials(P, deepest, deepest, st));
+        IST_CUDA(cudaStreamWaitEvent(st, P->ev_join, 0));
+    } else {
+        IST_TRY(run_forward(P, x_dev, deepest, st));
+        IST_TRY(run_loss_partials(P, 0, deepest, st));
+    }
+    IST_TRY(run_loss_finalize(P, losses_dev, st));
     Seeds S;
     S.use_losses = true;
     IST_TRY(run_backward(P, S, deepest, grad_dev, st));
