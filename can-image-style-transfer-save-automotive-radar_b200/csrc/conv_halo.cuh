@@ -182,7 +182,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // (the second cross buffer, so the cross terms are single-buffered in that case). Operand formats cannot be mixed inside
     // one MMA and the two products carry different scales, so the sum is formed in the epilogue: acc += alpha2[frame] * gram.
     const int xchunks = p.extra_chunks;
-    const int kiters = taps * cchunks;
     const int promote = p.promote < 1 ? 1 : p.promote;
     const bool split = (p.passes == 3);
     const bool halo = (taps == 9);
@@ -190,20 +189,45 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t a_tx = (uint32_t)(planes * (halo ? Cfg::HALO_BYTES : Cfg::EXACT_BYTES));
     const uint32_t b_tx = (uint32_t)(planes * Cfg::B_PLANE);
     const uint32_t a_sbo = halo ? (uint32_t)(Cfg::PW * 128) : 1024u;
+    const bool xsingle = xchunks > 0;             // single cross buffer when the second one holds the Gram accumulator
+
+    // Work distribution ("stream-K" over 64-channel chunks). A tile is CH = cchunks + xchunks chunk units; the G = tiles * CH
+    // units are cut into gridDim.x equal contiguous ranges, so that every SM gets the same amount of tensor work although
+    // the tile counts of the VGG layers (128, 256, 512, ...) never divide by 148. A CTA walks its range segment by segment;
+    // a segment that starts inside a tile (cbeg > 0; only the first segment of a CTA can) leaves its fp32 partial tile in
+    // p.sk_ws[blockIdx.x] and raises p.sk_flags[blockIdx.x]; the CTA that holds the head of a tile (cbeg == 0) adds the partials
+    // of the following CTAs in CTA order (fixed order: deterministic) and runs the epilogue. Partial producers never wait, and
+    // all CTAs are co-resident (grid <= number of SMs, one CTA per SM), so the waits cannot deadlock.
+    // Without a workspace the ranges are rounded to whole tiles (classic persistent tile loop).
+    const int CH = cchunks + xchunks;
+    int g_begin, g_end;                            // the host guarantees tiles * CH < 2^31
+    if (p.sk_ws != nullptr) {
+        const long long G = (long long)total_tiles * CH;
+        g_begin = (int)(G * blockIdx.x / gridDim.x);
+        g_end = (int)(G * (blockIdx.x + 1) / gridDim.x);
+    } else {
+        g_begin = (int)((long long)total_tiles * blockIdx.x / gridDim.x) * CH;
+        g_end = (int)((long long)total_tiles * (blockIdx.x + 1) / gridDim.x) * CH;
+    }
+#define IST_FOR_SEGMENTS(tile, cbeg, cend)                                                                     \
+    for (int g_ = g_begin, len_ = 0; g_ < g_end; g_ += len_)                                                    \
+        if (const int tile = g_ / CH; true)                                                                     \
+            if (const int cbeg = g_ - tile * CH; true)                                                          \
+                if (const int cend = (cbeg + (g_end - g_) < CH) ? (cbeg + (g_end - g_)) : CH; (len_ = cend - cbeg, true))
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer ------------------------------------------------
         if (lane == 0) {
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            IST_FOR_SEGMENTS(tile, cbeg, cend) {
                 const int tm = tile % tiles_m;
                 const int tn = tile / tiles_m;
                 const int tx = tm % p.tiles_x;
                 const int ty = (tm / p.tiles_x) % p.tiles_y;
                 const int fr = tm / (p.tiles_x * p.tiles_y);
                 const int x0 = tx * Cfg::TW - (halo ? 1 : 0), y0 = ty * Cfg::TH - (halo ? 1 : 0), n0 = tn * N_TILE;
-                for (int cc = 0; cc < cchunks + xchunks; ++cc) {
+                for (int cc = cbeg; cc < cend; ++cc) {
                     const bool ex = cc >= cchunks;
                     const int c64 = (ex ? cc - cchunks : cc) * 64;
                     mbar_wait(aempty(as), aph ^ 1u);
@@ -232,8 +256,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     } else if (warp == 1) {
         // ------------------------------------------ MMA issuer 1: hi*hi chains ------------------------------------------
         // Two warps issue MMAs (this one the short hi*hi chains, warp 6 the hi*lo + lo*hi cross terms): a single issuing
-        // thread sustains about one tcgen05.mma per ~100 cycles (measured), below the 64-cycle execution time of a
-        // 128x128x16 MMA, and the two streams write different accumulators, so they are independent.
+        // thread sustains about one tcgen05.mma per ~107 cycles (measured, tools/probes/umma_probe.cu), above the 64-cycle
+        // execution time of a 128x128x16 MMA; two streams that write different accumulators reach 86.
         // The whole warp walks the (warp-uniform) loop; one elected lane issues. Descriptors are a constant high word plus
         // a low word (start address >> 4) that only receives small adds.
         const uint32_t a_hi_w = ((a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
@@ -242,10 +266,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int kyn = halo ? 3 : 1;
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
-        uint32_t mcount = 0, tcount = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        uint32_t mcount = 0;
+        bool first = true;
+        IST_FOR_SEGMENTS(tile, cbeg, cend) {
+            (void)tile;
+            const int mend = cend < cchunks ? cend : cchunks;          // main chunks of the segment: [cbeg, mend)
+            const int kit_seg = (mend > cbeg ? mend - cbeg : 0) * taps;
             int kit = 0;
-            for (int cc = 0; cc < cchunks; ++cc) {
+            for (int cc = cbeg; cc < mend; ++cc) {
                 mbar_wait(afull(as), aph);
                 const uint32_t a_lo_stage = (a_base + as * Cfg::A_STAGE) >> 4;
                 for (int ky = 0; ky < kyn; ++ky) {
@@ -253,12 +281,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         const bool last_tap = (ky == kyn - 1 && kx == kyn - 1);
                         const int in_chain = kit % promote;
                         const uint32_t mb = mcount & 1u;
-                        const bool chain_end = (in_chain == promote - 1) || (kit == kiters - 1);
+                        const bool chain_end = (in_chain == promote - 1) || (kit == kit_seg - 1);
                         if (in_chain == 0) mbar_wait(mempty(mb), ((mcount >> 1) & 1u) ^ 1u);
                         mbar_wait(bfull(bs), bph);
                         tc_fence_after();
                         if (elect_one()) {
-                            if (dbg != nullptr && tcount == 0 && kit == 0) dbg[2] = clock64();
+                            if (dbg != nullptr && first) dbg[2] = clock64();
                             const uint32_t d_main = tmem_base + mb * N_TILE;
                             const uint32_t a_lo = a_lo_stage + (uint32_t)((ky * Cfg::PW + kx) * 8);
                             const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
@@ -268,9 +296,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                             if (chain_end) umma_commit(mfull(mb));
                             umma_commit(bempty(bs));
                             if (last_tap) umma_commit(aempty(as));
-                            if (dbg != nullptr && kit == kiters - 1) dbg[3] = clock64();
+                            if (dbg != nullptr) dbg[3] = clock64();
                         }
                         __syncwarp();
+                        first = false;
                         if (chain_end) ++mcount;
                         if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                     }
@@ -279,7 +308,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
             // fused Gram k-steps are issued by warp 6 alone; this warp only keeps the stage rings in step and contributes
             // its share of the release arrivals
-            for (int xc = 0; xc < xchunks; ++xc) {
+            for (int cc = (cbeg > cchunks ? cbeg : cchunks); cc < cend; ++cc) {
                 mbar_wait(afull(as), aph);
                 mbar_wait(bfull(bs), bph);
                 if (elect_one()) {
@@ -292,82 +321,89 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
         }
     } else if (warp == 6) {
-        // ------------------------------------- MMA issuer 2: hi*lo + lo*hi cross terms -----------------------------------
+        // ------------------------------ MMA issuer 2: hi*lo + lo*hi cross terms, fused Gram k-steps ----------------------
         if (split) {
             const uint32_t a_hi_w = ((a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
             const uint32_t b_hi_w = (1024u >> 4) | (1u << 14) | (2u << 29);
             const uint32_t idesc = p.idesc;
+            const uint32_t idesc2 = p.idesc2;
             const int kyn = halo ? 3 : 1;
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
-            uint32_t tcount = 0;
-            const bool xsingle = xchunks > 0;         // single cross buffer when the second one holds the Gram accumulator
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-                const uint32_t xa = xsingle ? 0u : (tcount & 1u);
-                const uint32_t xph = xsingle ? (tcount & 1u) : ((tcount >> 1) & 1u);
+            uint32_t scount = 0;
+            IST_FOR_SEGMENTS(tile, cbeg, cend) {
+                (void)tile;
+                const uint32_t xa = xsingle ? 0u : (scount & 1u);
+                const uint32_t xph = xsingle ? (scount & 1u) : ((scount >> 1) & 1u);
                 const uint32_t d_cross = tmem_base + (uint32_t)(2 * N_TILE) + xa * N_TILE;
                 const uint32_t d_gram = tmem_base + (uint32_t)(3 * N_TILE);
                 mbar_wait(xempty(xa), xph ^ 1u);
                 tc_fence_after();
-                int kit = 0;
-                for (int cc = 0; cc < cchunks; ++cc) {
+                int kit = 0, xc = 0;
+                for (int cc = cbeg; cc < cend; ++cc) {
+                    const bool ex = cc >= cchunks;
+                    const bool last_chunk = (cc == cend - 1);
                     mbar_wait(afull(as), aph);
                     const uint32_t a_lo_stage = (a_base + as * Cfg::A_STAGE) >> 4;
-                    for (int ky = 0; ky < kyn; ++ky) {
-                        for (int kx = 0; kx < kyn; ++kx, ++kit) {
-                            const bool last_tap = (ky == kyn - 1 && kx == kyn - 1);
-                            mbar_wait(bfull(bs), bph);
-                            tc_fence_after();
-                            if (elect_one()) {
-                                const uint32_t a_lo = a_lo_stage + (uint32_t)((ky * Cfg::PW + kx) * 8);
-                                const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
+                    if (!ex) {
+                        for (int ky = 0; ky < kyn; ++ky) {
+                            for (int kx = 0; kx < kyn; ++kx, ++kit) {
+                                const bool last_tap = (ky == kyn - 1 && kx == kyn - 1);
+                                mbar_wait(bfull(bs), bph);
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    const uint32_t a_lo = a_lo_stage + (uint32_t)((ky * Cfg::PW + kx) * 8);
+                                    const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
 #pragma unroll
-                                for (int k4 = 0; k4 < 4; ++k4) {
-                                    umma_f16_lh(d_cross, a_lo + 2 * k4, a_hi_w, b_lo + (Cfg::B_PLANE >> 4) + 2 * k4, b_hi_w, idesc,
-                                                (kit | k4) != 0 ? 1u : 0u);
-                                    umma_f16_lh(d_cross, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, 1u);
+                                    for (int k4 = 0; k4 < 4; ++k4) {
+                                        umma_f16_lh(d_cross, a_lo + 2 * k4, a_hi_w, b_lo + (Cfg::B_PLANE >> 4) + 2 * k4, b_hi_w, idesc,
+                                                    (kit | k4) != 0 ? 1u : 0u);
+                                        umma_f16_lh(d_cross, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, 1u);
+                                    }
+                                    umma_commit(bempty(bs));
+                                    if (last_tap) umma_commit(aempty(as));
+                                    if (last_tap && last_chunk) umma_commit(xfull(xa));
                                 }
-                                umma_commit(bempty(bs));
-                                if (last_tap) umma_commit(aempty(as));
-                                if (kit == kiters - 1 && xchunks == 0) umma_commit(xfull(xa));
+                                __syncwarp();
+                                if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                             }
-                            __syncwarp();
-                            if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                         }
-                    }
-                    if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
-                }
-                for (int xc = 0; xc < xchunks; ++xc) {
-                    mbar_wait(afull(as), aph);
-                    mbar_wait(bfull(bs), bph);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t a_lo = ((a_base + as * Cfg::A_STAGE) >> 4) + (uint32_t)((Cfg::PW + 1) * 8);   // centre tap
-                        const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
-                        const uint32_t idesc2 = p.idesc2;
+                    } else {
+                        mbar_wait(bfull(bs), bph);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t a_lo = a_lo_stage + (uint32_t)((Cfg::PW + 1) * 8);   // centre tap of the halo box
+                            const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            umma_f16_lh(d_gram, a_lo + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc2, (xc | k4) != 0 ? 1u : 0u);
-                            umma_f16_lh(d_gram, a_lo + 2 * k4, a_hi_w, b_lo + (Cfg::B_PLANE >> 4) + 2 * k4, b_hi_w, idesc2, 1u);
-                            umma_f16_lh(d_gram, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc2, 1u);
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                umma_f16_lh(d_gram, a_lo + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc2, (xc | k4) != 0 ? 1u : 0u);
+                                umma_f16_lh(d_gram, a_lo + 2 * k4, a_hi_w, b_lo + (Cfg::B_PLANE >> 4) + 2 * k4, b_hi_w, idesc2, 1u);
+                                umma_f16_lh(d_gram, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc2, 1u);
+                            }
+                            umma_commit(bempty(bs));
+                            umma_commit(aempty(as));
+                            if (last_chunk) umma_commit(xfull(xa));
                         }
-                        umma_commit(bempty(bs));
-                        umma_commit(aempty(as));
-                        if (xc == xchunks - 1) umma_commit(xfull(xa));
+                        __syncwarp();
+                        ++xc;
+                        if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                     if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
                 }
+                ++scount;
             }
         }
     } else {
         // ------------------------------------------- promotion + epilogue ---------------------------------------------
         const int quad = warp & 3;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const int nchains = (kiters + promote - 1) / promote;
-        uint32_t mcount = 0, tcount = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int m = quad * 32 + lane;                  // accumulator row == pixel inside the tile
+        uint32_t mcount = 0, scount = 0;
+        IST_FOR_SEGMENTS(tile, cbeg, cend) {
+            const int mend = cend < cchunks ? cend : cchunks;
+            const int kit_seg = (mend > cbeg ? mend - cbeg : 0) * taps;
+            const int nchains = (kit_seg + promote - 1) / promote;
+            const bool has_main = kit_seg > 0, has_extra = cend > cchunks;
             float acc[N_TILE];
 #pragma unroll
             for (int j = 0; j < N_TILE; ++j) acc[j] = 0.f;
@@ -386,23 +422,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 tc_fence_before();
                 mbar_arrive(mempty(mb));
             }
+            const int tm = tile % tiles_m;
+            const int tn = tile / tiles_m;
+            const int tx = tm % p.tiles_x;
+            const int ty = (tm / p.tiles_x) % p.tiles_y;
+            const int fr = tm / (p.tiles_x * p.tiles_y);
+            const int n0 = tn * N_TILE;
             if (split) {
-                const bool xsingle = xchunks > 0;
-                const uint32_t xa = xsingle ? 0u : (tcount & 1u);
-                mbar_wait(xfull(xa), xsingle ? (tcount & 1u) : ((tcount >> 1) & 1u));
+                const uint32_t xa = xsingle ? 0u : (scount & 1u);
+                mbar_wait(xfull(xa), xsingle ? (scount & 1u) : ((scount >> 1) & 1u));
                 tc_fence_after();
+                if (has_main) {
 #pragma unroll
-                for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(lane_base + (uint32_t)(2 * N_TILE) + xa * N_TILE + c0, r);
-                    tmem_ld_wait();
+                    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(lane_base + (uint32_t)(2 * N_TILE) + xa * N_TILE + c0, r);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+                        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+                    }
                 }
-                if (xsingle) {
+                if (has_extra) {
                     // fused Gram term: acc (true units, alpha == 1 for data-gradients) += alpha2[frame] * (D * F)
-                    const int frx = (tile % tiles_m) / (p.tiles_x * p.tiles_y);
-                    const float a2 = __ldg(p.alpha2_dev + frx);
+                    const float a2 = __ldg(p.alpha2_dev + fr);
 #pragma unroll
                     for (int c0 = 0; c0 < N_TILE; c0 += 32) {
                         uint32_t r[32];
@@ -415,14 +457,46 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 tc_fence_before();
                 mbar_arrive(xempty(xa));
             }
+            ++scount;
             if (dbg != nullptr && threadIdx.x == 64) dbg[4] = clock64();
-            const int tm = tile % tiles_m;
-            const int tn = tile / tiles_m;
-            const int tx = tm % p.tiles_x;
-            const int ty = (tm / p.tiles_x) % p.tiles_y;
-            const int fr = tm / (p.tiles_x * p.tiles_y);
-            const int n0 = tn * N_TILE;
-            const int m = quad * 32 + lane;                  // accumulator row == pixel inside the tile
+            if (cbeg != 0) {
+                // partial tile of a segment that starts inside a tile: hand it to the CTA that holds the tile's head
+                float* ws = p.sk_ws + (size_t)blockIdx.x * (128 * N_TILE);
+#pragma unroll
+                for (int j = 0; j < N_TILE; ++j) ws[j * 128 + m] = acc[j];
+                __threadfence();
+                named_bar_sync(1, 128);
+                if (threadIdx.x == 64) {
+                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + blockIdx.x), "r"(1) : "memory");
+                }
+                continue;
+            }
+            if (cend < CH) {
+                // head of a tile whose remaining chunks belong to the following CTAs: add their partials in CTA order
+                int covered = cend;
+                for (int oc = blockIdx.x + 1; covered < CH; ++oc) {
+                    const long long Gt = (long long)total_tiles * CH;
+                    const int ob = (int)(Gt * oc / gridDim.x), oe = (int)(Gt * (oc + 1) / gridDim.x);
+                    const int olen = (oe - ob) < (CH - covered) ? (oe - ob) : (CH - covered);
+                    if (threadIdx.x == 64) {
+                        int v = 0;
+                        uint32_t spins = 0;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.sk_flags + oc) : "memory");
+                            if (++spins > (1u << 26)) __trap();
+                        } while (v == 0);
+                    }
+                    named_bar_sync(1, 128);
+                    const float* ws = p.sk_ws + (size_t)oc * (128 * N_TILE);
+#pragma unroll
+                    for (int j = 0; j < N_TILE; ++j) acc[j] += __ldcg(ws + j * 128 + m);
+                    named_bar_sync(1, 128);
+                    if (threadIdx.x == 64) {
+                        asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + oc), "r"(0) : "memory");
+                    }
+                    covered += olen;
+                }
+            }
             float alpha = p.alpha;
             if (p.alpha_dev != nullptr) alpha *= __ldg(p.alpha_dev + (size_t)p.alpha_stride * fr);
             const int gx = tx * Cfg::TW + (m % Cfg::TW), gy = ty * Cfg::TH + (m / Cfg::TW);
@@ -477,6 +551,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
         if (p.use_tma_store && threadIdx.x == 64) tma_store_wait_all();
     }
+#undef IST_FOR_SEGMENTS
 
     tc_fence_before();
     __syncthreads();

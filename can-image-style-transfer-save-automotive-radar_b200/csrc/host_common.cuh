@@ -219,7 +219,8 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
         attr_done = true;
     }
     const int total = p.NB * p.tiles_x * p.tiles_y * p.tiles_n;
-    const int grid = total < num_sms() ? total : num_sms();
+    const long long units = (long long)total * (p.sk_ws != nullptr ? (p.Cin / 64 + p.extra_chunks) : 1);
+    const int grid = units < num_sms() ? (int)units : num_sms();
     const double px = (double)p.NB * p.H * p.W;
     const int planes = p.passes == 3 ? 2 : 1;
     launch_pre(p.taps == 9 ? (p.mode == CONV_FWD ? "conv_halo_fwd" : "conv_halo_dgrad") : "conv_halo_gram_bwd",
@@ -264,6 +265,33 @@ inline int promote_steps() {
     return v;
 }
 // Fills the tiling fields of p (NB,H,W,Cin,Cout,taps,passes,mode and epilogue pointers must be set) and launches.
+// Stream-K workspace of the conv_halo kernel: one fp32 partial tile + one flag per CTA. One instance per plan (kernels of a
+// plan run on one stream); the per-op entry points share a process-wide one. IST_B200_NO_STREAMK=1 disables the split.
+struct ConvWorkspace {
+    float* ws = nullptr;
+    int* flags = nullptr;
+    int alloc() {
+        if (ws != nullptr) return IST_OK;
+        const char* e = getenv("IST_B200_NO_STREAMK");
+        if (e != nullptr && atoi(e) == 1) return IST_OK;
+        const size_t n = (size_t)num_sms();
+        cudaError_t r = cudaMalloc(&ws, n * 128 * 128 * sizeof(float));
+        if (r == cudaSuccess) r = cudaMalloc(&flags, n * sizeof(int));
+        if (r == cudaSuccess) r = cudaMemset(flags, 0, n * sizeof(int));
+        if (r != cudaSuccess) return fail(IST_ERR_CUDA, "stream-K workspace allocation failed: %s", cudaGetErrorString(r));
+        return IST_OK;
+    }
+    void release() {
+        if (ws != nullptr) cudaFree(ws);
+        if (flags != nullptr) cudaFree(flags);
+        ws = nullptr; flags = nullptr;
+    }
+};
+inline ConvWorkspace& global_conv_workspace() {
+    static ConvWorkspace w;
+    return w;
+}
+
 // o_hi / o_lo: optional tensor maps (map_act(..., taps = 1)) of the output planes; with them the conv_halo forward epilogue
 // leaves through shared memory + TMA store.
 // fmt: operand format of the k-steps, 0 = fp16 x fp16, 1 = bf16 x bf16 (mixing the two in one MMA is an illegal instruction on sm_100a)
@@ -272,7 +300,7 @@ inline uint32_t conv_idesc(int fmt, int nt) {
 }
 inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                        const CUtensorMap& b_lo, ConvParams p, int fmt, const CUtensorMap* o_hi = nullptr,
-                       const CUtensorMap* o_lo = nullptr, const GramFuse* gf = nullptr) {
+                       const CUtensorMap* o_lo = nullptr, const GramFuse* gf = nullptr, ConvWorkspace* wsp = nullptr) {
     if (p.Cin % 64 != 0 || p.Cout % 64 != 0) return fail(IST_ERR_ARG, "conv_igemm needs Cin, Cout %% 64 == 0 (got %d, %d)", p.Cin, p.Cout);
     pick_tile(p.W, &p.TW, &p.TH);
     p.tiles_x = (p.W + p.TW - 1) / p.TW;
@@ -292,6 +320,19 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
             p.alpha2_dev = gf->alpha;
         }
         p.dbg_flags = halo_dbg_flags();
+        if (wsp == nullptr) wsp = &global_conv_workspace();
+        IST_TRY(wsp->alloc());
+        // stream-K pays (partial-tile exchange, more segments) only when whole-tile waves leave SMs idle: tiles / SMs far from
+        // an integer, and at least two chunk units per tile to split
+        {
+            const long long tiles = (long long)p.NB * p.tiles_x * p.tiles_y * p.tiles_n;
+            const int ch = p.Cin / 64 + p.extra_chunks;
+            const long long waves = (tiles + num_sms() - 1) / num_sms();
+            const double eff = (double)tiles / (double)(waves * num_sms());
+            const bool want = ch >= 2 && eff < 0.93 && tiles * ch < (1ll << 30);
+            p.sk_ws = want ? wsp->ws : nullptr;
+            p.sk_flags = want ? wsp->flags : nullptr;
+        }
         p.use_tma_store = (p.out_f32 == nullptr && o_hi != nullptr && o_lo != nullptr) ? 1 : 0;
         const CUtensorMap& oh = p.use_tma_store ? *o_hi : a_hi;
         const CUtensorMap& ol = p.use_tma_store ? *o_lo : a_lo;

@@ -74,7 +74,9 @@ struct ist_plan {
     // tiles to fill the GPU, is computed)
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    ConvWorkspace skw;             // stream-K partial tiles of the conv kernel
     ~ist_plan() {
+        skw.release();
         if (ev_fork != nullptr) cudaEventDestroy(ev_fork);
         if (ev_join != nullptr) cudaEventDestroy(ev_join);
         if (side != nullptr) cudaStreamDestroy(side);
@@ -124,7 +126,7 @@ int run_forward(ist_plan* P, const float* x, int upto, cudaStream_t st, int from
                 p.bias = L.bias;
                 p.out_scale = kActScale;
                 p.out_hi = L.out.hi; p.out_lo = L.out.lo;
-                IST_TRY(launch_conv(st, L.mA_hi, L.mA_lo, L.mBf_hi, L.mBf_lo, p, 0, &L.mO_hi, &L.mO_lo));
+                IST_TRY(launch_conv(st, L.mA_hi, L.mA_lo, L.mBf_hi, L.mBf_lo, p, 0, &L.mO_hi, &L.mO_lo, nullptr, &P->skw));
             }
         } else {
             const Layer& I = P->layers[l - 1];
@@ -207,7 +209,7 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         p.NB = NB; p.H = Cj.H; p.W = Cj.W; p.Cin = Cj.cout; p.Cout = Cj.cin; p.taps = 9;
         p.passes = P->passes_bwd; p.mode = CONV_GRAD; p.alpha = 1.f;
         return launch_conv(st, Cj.mG_hi, Cj.mG_lo, Cj.mBd_hi, Cj.mBd_lo, p, 1, dst != nullptr ? &dst->mGo_hi : nullptr,
-                           dst != nullptr ? &dst->mGo_lo : nullptr, gf);
+                           dst != nullptr ? &dst->mGo_lo : nullptr, gf, &P->skw);
     };
     auto gram_bwd = [&](Layer& L, const float* addend, bool content) -> int {
         ConvParams p;
@@ -219,7 +221,7 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         if (content) set_content(L, &p.f_hi, &p.f_lo, &p.t_hi, &p.t_lo, &p.content_coef);
         p.mask_hi = L.out.hi;
         p.out_hi = L.dY.hi; p.out_lo = L.dY.lo;
-        return launch_conv(st, L.mFeat_hi, L.mFeat_lo, L.mD_hi, L.mD_lo, p, 0, &L.mGo_hi, &L.mGo_lo);
+        return launch_conv(st, L.mFeat_hi, L.mFeat_lo, L.mD_hi, L.mD_lo, p, 0, &L.mGo_hi, &L.mGo_lo, nullptr, &P->skw);
     };
     auto route = [&](Layer& L, const float* g_pool, const float* addend, bool content, bool to_f32, float* f32_out) -> int {
         RouteParams r;
