@@ -144,7 +144,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     long long* dbg = p.dbg_times != nullptr ? p.dbg_times + 8 * (size_t)blockIdx.x : nullptr;
-    if (dbg != nullptr && threadIdx.x == 0) dbg[0] = clock64();
+    unsigned long long gt0 = 0;
+    if (dbg != nullptr && threadIdx.x == 0) {
+        dbg[0] = clock64();
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+    }
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA_hi);
@@ -555,7 +559,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
-    if (dbg != nullptr && threadIdx.x == 0) dbg[6] = clock64();
+    if (dbg != nullptr && threadIdx.x == 0) {
+        dbg[6] = clock64();
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
+        dbg[7] = (long long)(gt1 - gt0);          // nanoseconds: with dbg[6] - dbg[0] gives the SM clock actually running
+    }
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);

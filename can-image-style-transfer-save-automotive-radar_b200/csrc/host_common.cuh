@@ -241,11 +241,14 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
         std::vector<long long> h(8 * (size_t)grid);
         IST_CUDA(cudaMemcpy(h.data(), dbuf, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost));
         double sum[7] = {0, 0, 0, 0, 0, 0, 0};
-        for (int c = 0; c < grid; ++c)
+        double ns = 0;
+        for (int c = 0; c < grid; ++c) {
             for (int k = 1; k < 7; ++k) sum[k] += (double)(h[8 * c + k] - h[8 * c]);
-        fprintf(stderr, "[dbg] conv %dx%d %d->%d taps %d passes %d promote %d grid %d tiles %d | avg clk since entry: setup %.0f first_mma %.0f last_issue %.0f acc_read %.0f stored %.0f exit %.0f\n",
+            ns += (double)h[8 * c + 7];
+        }
+        fprintf(stderr, "[dbg] conv %dx%d %d->%d taps %d passes %d promote %d grid %d tiles %d | avg clk since entry: setup %.0f first_mma %.0f last_issue %.0f acc_read %.0f stored %.0f exit %.0f | %.1f us -> SM clock %.0f MHz\n",
                 p.H, p.W, p.Cin, p.Cout, p.taps, p.passes, p.promote, grid, total, sum[1] / grid, sum[2] / grid, sum[3] / grid,
-                sum[4] / grid, sum[5] / grid, sum[6] / grid);
+                sum[4] / grid, sum[5] / grid, sum[6] / grid, ns / grid * 1e-3, sum[6] / ns * 1e3);
         launch_post(st);
         return IST_OK;
     }
