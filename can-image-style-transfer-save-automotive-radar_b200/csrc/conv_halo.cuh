@@ -176,8 +176,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t tmem_base = *tmem_slot_gen;
     if (dbg != nullptr && threadIdx.x == 0) dbg[1] = clock64();
 
-    const int tiles_m = p.NB * p.tiles_y * p.tiles_x;
-    const int total_tiles = tiles_m * p.tiles_n;
     const int cchunks = p.Cin >> 6;
     const int taps = p.taps;
     // Fused Gram backward (style layers): after the taps * cchunks k-steps of the convolution, `extra_chunks` more k-steps
@@ -195,41 +193,51 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t a_sbo = halo ? (uint32_t)(Cfg::PW * 128) : 1024u;
     const bool xsingle = xchunks > 0;             // single cross buffer when the second one holds the Gram accumulator
 
-    // Work distribution ("stream-K" over 64-channel chunks). A tile is CH = cchunks + xchunks chunk units; the G = tiles * CH
-    // units are cut into gridDim.x equal contiguous ranges, so that every SM gets the same amount of tensor work although
-    // the tile counts of the VGG layers (128, 256, 512, ...) never divide by 148. A CTA walks its range segment by segment;
-    // a segment that starts inside a tile (cbeg > 0; only the first segment of a CTA can) leaves its fp32 partial tile in
-    // p.sk_ws[blockIdx.x] and raises p.sk_flags[blockIdx.x]; the CTA that holds the head of a tile (cbeg == 0) adds the partials
-    // of the following CTAs in CTA order (fixed order: deterministic) and runs the epilogue. Partial producers never wait, and
-    // all CTAs are co-resident (grid <= number of SMs, one CTA per SM), so the waits cannot deadlock.
+    // Work distribution ("stream-K" over 64-channel chunks), frame by frame. A tile is CH = cchunks + xchunks chunk units; the
+    // Gf = tiles_per_frame * CH units of ONE frame are cut into `cpf` equal contiguous ranges (cpf = CTAs per frame, chosen by
+    // the host from the frame geometry only), so that every SM gets the same amount of tensor work although the tile counts of
+    // the VGG layers (128, 256, 512, ...) never divide by 148. gridDim.x / cpf frame groups work on different frames at the
+    // same time. A CTA walks its range segment by segment; a segment that starts inside a tile (cbeg > 0; only the first
+    // segment of a range can) leaves its fp32 partial tile in p.sk_ws and raises a flag; the CTA that holds the head of a tile
+    // (cbeg == 0) adds the partials of the following CTAs in CTA order and runs the epilogue. The partition, hence the
+    // rounding, of a frame is the same whatever the batch size; all sums have a fixed order (deterministic).
+    // Partial producers wait only for their own previous-but-one partial to be consumed, heads wait only for producers with
+    // a higher CTA index, and all CTAs are co-resident (grid <= number of SMs, one CTA per SM): the waits cannot deadlock.
     // Without a workspace the ranges are rounded to whole tiles (classic persistent tile loop).
     const int CH = cchunks + xchunks;
-    int g_begin, g_end;                            // the host guarantees tiles * CH < 2^31
+    const int tiles_xy = p.tiles_y * p.tiles_x;
+    const int tiles_f = tiles_xy * p.tiles_n;          // tiles of one frame
+    const int cpf = p.sk_cpf;
+    const int nfg = gridDim.x / cpf;                   // frame groups
+    const int fgroup = blockIdx.x / cpf, lid = blockIdx.x - fgroup * cpf;
+    int g_begin, g_end;                                // the host guarantees tiles_f * CH < 2^31
     if (p.sk_ws != nullptr) {
-        const long long G = (long long)total_tiles * CH;
-        g_begin = (int)(G * blockIdx.x / gridDim.x);
-        g_end = (int)(G * (blockIdx.x + 1) / gridDim.x);
+        const long long G = (long long)tiles_f * CH;
+        g_begin = (int)(G * lid / cpf);
+        g_end = (int)(G * (lid + 1) / cpf);
     } else {
-        g_begin = (int)((long long)total_tiles * blockIdx.x / gridDim.x) * CH;
-        g_end = (int)((long long)total_tiles * (blockIdx.x + 1) / gridDim.x) * CH;
+        g_begin = (int)((long long)tiles_f * lid / cpf) * CH;
+        g_end = (int)((long long)tiles_f * (lid + 1) / cpf) * CH;
     }
-#define IST_FOR_SEGMENTS(tile, cbeg, cend)                                                                     \
-    for (int g_ = g_begin, len_ = 0; g_ < g_end; g_ += len_)                                                    \
-        if (const int tile = g_ / CH; true)                                                                     \
-            if (const int cbeg = g_ - tile * CH; true)                                                          \
-                if (const int cend = (cbeg + (g_end - g_) < CH) ? (cbeg + (g_end - g_)) : CH; (len_ = cend - cbeg, true))
+    if (blockIdx.x >= nfg * cpf) g_end = g_begin;      // surplus CTAs (grid not a multiple of cpf) have no work
+#define IST_FOR_SEGMENTS(fr, fcount, tile, cbeg, cend)                                                          \
+    for (int fr = fgroup, fcount = 0; fr < p.NB; fr += nfg, ++fcount)                                            \
+        for (int g_ = g_begin, len_ = 0; g_ < g_end; g_ += len_)                                                 \
+            if (const int tile = g_ / CH; true)                                                                  \
+                if (const int cbeg = g_ - tile * CH; true)                                                       \
+                    if (const int cend = (cbeg + (g_end - g_) < CH) ? (cbeg + (g_end - g_)) : CH; (len_ = cend - cbeg, true))
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer ------------------------------------------------
         if (lane == 0) {
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
-            IST_FOR_SEGMENTS(tile, cbeg, cend) {
-                const int tm = tile % tiles_m;
-                const int tn = tile / tiles_m;
-                const int tx = tm % p.tiles_x;
-                const int ty = (tm / p.tiles_x) % p.tiles_y;
-                const int fr = tm / (p.tiles_x * p.tiles_y);
+            IST_FOR_SEGMENTS(fr, fcount, tile, cbeg, cend) {
+                (void)fcount;
+                const int tn = tile / tiles_xy;
+                const int tm = tile - tn * tiles_xy;
+                const int ty = tm / p.tiles_x;
+                const int tx = tm - ty * p.tiles_x;
                 const int x0 = tx * Cfg::TW - (halo ? 1 : 0), y0 = ty * Cfg::TH - (halo ? 1 : 0), n0 = tn * N_TILE;
                 for (int cc = cbeg; cc < cend; ++cc) {
                     const bool ex = cc >= cchunks;
@@ -272,8 +280,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         uint32_t aph = 0, bph = 0;
         uint32_t mcount = 0;
         bool first = true;
-        IST_FOR_SEGMENTS(tile, cbeg, cend) {
-            (void)tile;
+        IST_FOR_SEGMENTS(fr, fcount, tile, cbeg, cend) {
+            (void)tile; (void)fr; (void)fcount;
             const int mend = cend < cchunks ? cend : cchunks;          // main chunks of the segment: [cbeg, mend)
             const int kit_seg = (mend > cbeg ? mend - cbeg : 0) * taps;
             int kit = 0;
@@ -335,8 +343,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
             uint32_t scount = 0;
-            IST_FOR_SEGMENTS(tile, cbeg, cend) {
-                (void)tile;
+            IST_FOR_SEGMENTS(fr, fcount, tile, cbeg, cend) {
+                (void)tile; (void)fr; (void)fcount;
                 const uint32_t xa = xsingle ? 0u : (scount & 1u);
                 const uint32_t xph = xsingle ? (scount & 1u) : ((scount >> 1) & 1u);
                 const uint32_t d_cross = tmem_base + (uint32_t)(2 * N_TILE) + xa * N_TILE;
@@ -403,7 +411,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
         const int m = quad * 32 + lane;                  // accumulator row == pixel inside the tile
         uint32_t mcount = 0, scount = 0;
-        IST_FOR_SEGMENTS(tile, cbeg, cend) {
+        IST_FOR_SEGMENTS(fr, fcount, tile, cbeg, cend) {
             const int mend = cend < cchunks ? cend : cchunks;
             const int kit_seg = (mend > cbeg ? mend - cbeg : 0) * taps;
             const int nchains = (kit_seg + promote - 1) / promote;
@@ -426,11 +434,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 tc_fence_before();
                 mbar_arrive(mempty(mb));
             }
-            const int tm = tile % tiles_m;
-            const int tn = tile / tiles_m;
-            const int tx = tm % p.tiles_x;
-            const int ty = (tm / p.tiles_x) % p.tiles_y;
-            const int fr = tm / (p.tiles_x * p.tiles_y);
+            const int tn = tile / tiles_xy;
+            const int tm = tile - tn * tiles_xy;
+            const int ty = tm / p.tiles_x;
+            const int tx = tm - ty * p.tiles_x;
             const int n0 = tn * N_TILE;
             if (split) {
                 const uint32_t xa = xsingle ? 0u : (scount & 1u);
@@ -463,40 +470,54 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
             ++scount;
             if (dbg != nullptr && threadIdx.x == 64) dbg[4] = clock64();
+            const int slot = fcount & 1;                  // partial tiles are double-buffered over the frames a CTA walks
             if (cbeg != 0) {
                 // partial tile of a segment that starts inside a tile: hand it to the CTA that holds the tile's head
-                float* ws = p.sk_ws + (size_t)blockIdx.x * (128 * N_TILE);
+                int* flag = p.sk_flags + 2 * blockIdx.x + slot;
+                if (threadIdx.x == 64) {                  // the partial of two frames ago must have been consumed
+                    int v = 1;
+                    uint32_t spins = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                        if (++spins > (1u << 26)) __trap();
+                    } while (v != 0);
+                }
+                named_bar_sync(1, 128);
+                float* ws = p.sk_ws + (size_t)(2 * blockIdx.x + slot) * (128 * N_TILE);
 #pragma unroll
                 for (int j = 0; j < N_TILE; ++j) ws[j * 128 + m] = acc[j];
                 __threadfence();
                 named_bar_sync(1, 128);
                 if (threadIdx.x == 64) {
-                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + blockIdx.x), "r"(1) : "memory");
+                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
                 }
                 continue;
             }
             if (cend < CH) {
-                // head of a tile whose remaining chunks belong to the following CTAs: add their partials in CTA order
+                // head of a tile whose remaining chunks belong to the following CTAs of this frame group: add their partials
+                // in CTA order
                 int covered = cend;
-                for (int oc = blockIdx.x + 1; covered < CH; ++oc) {
-                    const long long Gt = (long long)total_tiles * CH;
-                    const int ob = (int)(Gt * oc / gridDim.x), oe = (int)(Gt * (oc + 1) / gridDim.x);
+                for (int ol = lid + 1; covered < CH; ++ol) {
+                    const long long Gt = (long long)tiles_f * CH;
+                    const int ob = (int)(Gt * ol / cpf), oe = (int)(Gt * (ol + 1) / cpf);
                     const int olen = (oe - ob) < (CH - covered) ? (oe - ob) : (CH - covered);
+                    const int oc = fgroup * cpf + ol;
+                    int* flag = p.sk_flags + 2 * oc + slot;
                     if (threadIdx.x == 64) {
                         int v = 0;
                         uint32_t spins = 0;
                         do {
-                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.sk_flags + oc) : "memory");
+                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
                             if (++spins > (1u << 26)) __trap();
                         } while (v == 0);
                     }
                     named_bar_sync(1, 128);
-                    const float* ws = p.sk_ws + (size_t)oc * (128 * N_TILE);
+                    const float* ws = p.sk_ws + (size_t)(2 * oc + slot) * (128 * N_TILE);
 #pragma unroll
                     for (int j = 0; j < N_TILE; ++j) acc[j] += __ldcg(ws + j * 128 + m);
                     named_bar_sync(1, 128);
                     if (threadIdx.x == 64) {
-                        asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + oc), "r"(0) : "memory");
+                        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(0) : "memory");
                     }
                     covered += olen;
                 }

@@ -46,8 +46,9 @@ struct ConvParams {
     int extra_chunks;      // conv_halo: fused Gram-backward k-steps appended to the convolution (0 = none)
     uint32_t idesc2;       // instruction descriptor of those k-steps (fp16 features x fp16 D matrix)
     const float* alpha2_dev;   // [NB] multiplier of the fused Gram accumulator
-    float* sk_ws;          // conv_halo stream-K: [gridDim.x][128 * N_TILE] fp32 partial tiles (nullptr = whole-tile ranges)
-    int* sk_flags;         // [gridDim.x] partial-ready flags, zero between launches
+    float* sk_ws;          // conv_halo stream-K: [gridDim.x][2][128 * N_TILE] fp32 partial tiles (nullptr = whole-tile ranges)
+    int* sk_flags;         // [gridDim.x][2] partial-ready flags, zero between launches
+    int sk_cpf;            // CTAs that share one frame (gridDim.x / sk_cpf frame groups run side by side)
     int use_tma_store;     // conv_halo, CONV_FWD: the fp16 planes leave through shared memory + TMA store (tmO_hi / tmO_lo)
     int dbg_flags;         // timing experiments only: 2 = skip the A loads, 4 = skip the B loads (results are then garbage)
     long long* dbg_times;  // optional [gridDim.x][8] clock64 stamps of the kernel phases (IST_B200_DBG_TIMES=1)

@@ -219,8 +219,10 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
         attr_done = true;
     }
     const int total = p.NB * p.tiles_x * p.tiles_y * p.tiles_n;
-    const long long units = (long long)total * (p.sk_ws != nullptr ? (p.Cin / 64 + p.extra_chunks) : 1);
-    const int grid = units < num_sms() ? (int)units : num_sms();
+    int groups = num_sms() / p.sk_cpf;                 // frame groups that fit side by side
+    if (groups > p.NB) groups = p.NB;
+    if (groups < 1) groups = 1;
+    const int grid = groups * p.sk_cpf;
     const double px = (double)p.NB * p.H * p.W;
     const int planes = p.passes == 3 ? 2 : 1;
     launch_pre(p.taps == 9 ? (p.mode == CONV_FWD ? "conv_halo_fwd" : "conv_halo_dgrad") : "conv_halo_gram_bwd",
@@ -278,9 +280,9 @@ struct ConvWorkspace {
         const char* e = getenv("IST_B200_NO_STREAMK");
         if (e != nullptr && atoi(e) == 1) return IST_OK;
         const size_t n = (size_t)num_sms();
-        cudaError_t r = cudaMalloc(&ws, n * 128 * 128 * sizeof(float));
-        if (r == cudaSuccess) r = cudaMalloc(&flags, n * sizeof(int));
-        if (r == cudaSuccess) r = cudaMemset(flags, 0, n * sizeof(int));
+        cudaError_t r = cudaMalloc(&ws, n * 2 * 128 * 128 * sizeof(float));
+        if (r == cudaSuccess) r = cudaMalloc(&flags, n * 2 * sizeof(int));
+        if (r == cudaSuccess) r = cudaMemset(flags, 0, n * 2 * sizeof(int));
         if (r != cudaSuccess) return fail(IST_ERR_CUDA, "stream-K workspace allocation failed: %s", cudaGetErrorString(r));
         return IST_OK;
     }
@@ -326,15 +328,18 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
         if (wsp == nullptr) wsp = &global_conv_workspace();
         IST_TRY(wsp->alloc());
         // stream-K pays (partial-tile exchange, more segments) only when whole-tile waves leave SMs idle: tiles / SMs far from
-        // an integer, and at least two chunk units per tile to split
+        // an integer, and at least two chunk units per tile to split. Decided from ONE frame's geometry, so that the partition
+        // (hence the rounding) of a frame does not depend on the batch size.
         {
-            const long long tiles = (long long)p.NB * p.tiles_x * p.tiles_y * p.tiles_n;
+            const long long tiles_f = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
             const int ch = p.Cin / 64 + p.extra_chunks;
-            const long long waves = (tiles + num_sms() - 1) / num_sms();
-            const double eff = (double)tiles / (double)(waves * num_sms());
-            const bool want = ch >= 2 && eff < 0.93 && tiles * ch < (1ll << 30);
+            const long long waves = (tiles_f + num_sms() - 1) / num_sms();
+            const double eff = (double)tiles_f / (double)(waves * num_sms());
+            const bool want = wsp->ws != nullptr && ch >= 2 && eff < 0.93 && tiles_f * ch < (1ll << 30);
             p.sk_ws = want ? wsp->ws : nullptr;
             p.sk_flags = want ? wsp->flags : nullptr;
+            const long long units = want ? tiles_f * ch : tiles_f;
+            p.sk_cpf = units < num_sms() ? (int)units : num_sms();
         }
         p.use_tma_store = (p.out_f32 == nullptr && o_hi != nullptr && o_lo != nullptr) ? 1 : 0;
         const CUtensorMap& oh = p.use_tma_store ? *o_hi : a_hi;
@@ -365,11 +370,14 @@ inline int launch_conv_first_dgrad(cudaStream_t st, const uint16_t* g_hi, const 
     return IST_OK;
 }
 
+// The pixel split of a frame's Gram matrix depends on the frame geometry only, never on the batch size: every frame of a batch
+// is reduced with the partition (hence the rounding) of its single-frame run.
 inline void gram_split_plan(int NB, int HW, int C, int* splits, int* chunks_per_split) {
+    (void)NB;
     const int tiles_c = (C + 127) / 128;
     const int tri = tiles_c * (tiles_c + 1) / 2;
     const int total_chunks = (HW + 63) / 64;
-    int want = (num_sms() + tri * NB - 1) / (tri * NB);     // ~one CTA per SM; accuracy does not depend on the split (register promotion)
+    int want = (num_sms() + tri - 1) / tri;     // ~one CTA per SM for one frame; accuracy does not depend on the split (register promotion)
     if (want < 1) want = 1;
     if (want > total_chunks) want = total_chunks;
     if (want > 160) want = 160;

@@ -18,7 +18,7 @@ from PIL import Image
 
 from .config import get_cfg_defaults
 from .model import build_model
-from .model.engine import do_transfer_style
+from .model.engine import do_transfer_style, do_transfer_style_batch
 from .model.engine.hr_transfer_style import do_hr_transfer_style
 from .model.meta_arch import GramMSELoss, StyleTransfer
 from .parallel import gather_frames, init_distributed, shard_indices
@@ -82,6 +82,8 @@ def main(argv=None):
     parser.add_argument("--output-dir", default="./output/full_transfer/", help="where the stylised frames go")
     parser.add_argument("--max-frames", type=int, default=0, help="process at most this many frames (0 = all)")
     parser.add_argument("--high-resolution", action="store_true", help="run the coarse-to-fine second stage")
+    parser.add_argument("--frames-per-batch", type=int, default=1,
+                        help="optimise this many (independent, equally sized) frames side by side on each GPU")
     parser.add_argument("opts", help="Modify config options using the command-line", default=None, nargs=argparse.REMAINDER)
     args = parser.parse_args(argv)
 
@@ -107,15 +109,21 @@ def main(argv=None):
     mine = shard_indices(len(frames), rank, world)
     t_all = time.time()
     results = []
-    for i in mine:
+    fpb = max(1, args.frames_per_batch)
+    for b0 in range(0, len(mine), fpb):
+        group = mine[b0:b0 + fpb]
         start = time.time()
-        content_image = Image.open(frames[i]).convert('RGB')
-        out_image = do_transfer_style(cfg, model, content_image, style_image, device)
-        if args.high_resolution:
-            out_image = do_hr_transfer_style(cfg, model, content_image, style_image, out_image, device)
-        out_image.save(os.path.join(cfg.OUTPUT.DIR, os.path.basename(frames[i])))
-        results.append(torch.from_numpy(np.asarray(out_image).copy()))
-        logger.info("frame %s: %f second per frame" % (os.path.basename(frames[i]), time.time() - start))
+        contents = [Image.open(frames[i]).convert('RGB') for i in group]
+        if len(group) == 1:
+            outs = [do_transfer_style(cfg, model, contents[0], style_image, device)]
+        else:
+            outs = do_transfer_style_batch(cfg, model, contents, style_image, device)
+        for i, content_image, out_image in zip(group, contents, outs):
+            if args.high_resolution:
+                out_image = do_hr_transfer_style(cfg, model, content_image, style_image, out_image, device)
+            out_image.save(os.path.join(cfg.OUTPUT.DIR, os.path.basename(frames[i])))
+            results.append(torch.from_numpy(np.asarray(out_image).copy()))
+        logger.info("frames %s: %f second per frame" % ([os.path.basename(frames[i]) for i in group], (time.time() - start) / len(group)))
     if world > 1 and results:
         local = torch.stack(results).to(device)
         gathered = gather_frames(local, len(frames), rank, world)

@@ -1,6 +1,8 @@
-"""Per-frame orchestration with the reference's signature (IST/model/engine/transfer_style.py:11-44)."""
+"""Per-frame orchestration with the reference's signature (IST/model/engine/transfer_style.py:11-44), plus a batched variant
+for the frame loop of IST/main.py:186-238 (independent frames of equal size optimised side by side on one GPU)."""
 import os
 
+import torch
 from torch.autograd import Variable
 
 from ...data import ImageTransform
@@ -29,3 +31,23 @@ def do_transfer_style(cfg, model, content_image, style_image, device, content_on
     os.makedirs(cfg.OUTPUT.DIR, exist_ok=True)
     out_image.save(cfg.OUTPUT.DIR + cfg.OUTPUT.FILE_NAME)
     return out_image
+
+
+def do_transfer_style_batch(cfg, model, content_images, style_image, device, style_tensor=None):
+    """Several content frames against one shared style image (IST/main.py:184-238 processes them one at a time). Every frame
+    is its own optimisation problem with its own L-BFGS state — results equal the per-frame calls — but the frames share each
+    kernel launch, which fills the GPU on the deep VGG layers. All frames must have the same size after the transform.
+    `style_tensor` (the already transformed style image) may be passed to reuse the cached Gram targets across calls."""
+    logger.info("Start transferring a batch of %d frames." % len(content_images))
+    image_transformer = ImageTransform(cfg.DATA.IMG_SIZE, cfg.DATA.IMAGENET_MEAN)
+    contents = [transform_image(image_transformer, im, device) for im in content_images]
+    shapes = {tuple(c.shape) for c in contents}
+    if len(shapes) != 1:
+        raise ValueError("do_transfer_style_batch: frames of different sizes cannot share a batch: %s" % sorted(shapes))
+    content = torch.cat(contents, dim=0).contiguous()
+    if style_tensor is None:
+        style_tensor = transform_image(image_transformer, style_image, device)
+    optimized = Variable(content.data.clone(), requires_grad=True)
+    optimized = optimize_new(model, content, style_tensor, optimized, cfg, cfg.LOSS.MAX_ITER)
+    out = optimized.data.cpu()
+    return [image_transformer.post_preparation(out[i].squeeze()) for i in range(out.shape[0])]

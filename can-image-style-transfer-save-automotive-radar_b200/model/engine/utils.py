@@ -49,19 +49,21 @@ def _deepest(vgg, keys):
 
 
 def style_targets(vgg, style_image, style_keys):
-    """Gram targets of the style image, cached on the VGG module per (style tensor, layer set, weights)."""
+    """Gram targets of the style image, cached on the VGG module for the style tensor last used (same tensor object, same
+    version counter, same layer set and weights). The cache holds a reference to the tensor, so its storage cannot be
+    recycled for a different image while the entry is alive."""
     cache = vgg.__dict__.setdefault('_style_target_cache', {})
-    key = (style_image.data_ptr(), style_image._version, tuple(style_image.shape), tuple(style_keys), vgg._token())
-    hit = cache.get(key)
+    hit = cache.get('entry')
     if hit is not None:
-        return hit
+        ref, version, keys, token, grams = hit
+        if ref is style_image and version == style_image._version and keys == tuple(style_keys) and token == vgg._token():
+            return grams
     b, _, hs, ws = style_image.shape
     with torch.no_grad():
         splan = vgg.plan(b, hs, ws, _deepest(vgg, style_keys), device=style_image.device)
         splan.forward(style_image.contiguous().float(), _deepest(vgg, style_keys))
         grams = [splan.gram(k) for k in style_keys]
-    cache.clear()                       # one live style at a time (main.py:184 uses a single style image)
-    cache[key] = grams
+    cache['entry'] = (style_image, style_image._version, tuple(style_keys), vgg._token(), grams)   # one live style (main.py:184)
     return grams
 
 

@@ -112,3 +112,21 @@ def test_frame_functions_with_pil(model_cfg, tmp_path):
     hr = do_hr_transfer_style(cfg, model, content, style, out, dev)
     assert hr.size == (96, 96) and (tmp_path / cfg.OUTPUT.HR_FILE_NAME).exists()
     assert np.asarray(hr).std() > 0
+
+
+def test_batched_frames_equal_per_frame_calls(model_cfg, tmp_path):
+    """do_transfer_style_batch == one do_transfer_style per frame (independent problems; at this size every layer's work split
+    is the same for 1 and 3 frames, so the kernels round identically — see DESIGN.md 3 for large images)."""
+    from ist_b200.model.engine import do_transfer_style_batch
+    cfg, model = model_cfg
+    cfg = cfg.clone()
+    cfg.DATA.IMG_SIZE = 64
+    cfg.LOSS.MAX_ITER = 20
+    cfg.OUTPUT.DIR = str(tmp_path) + "/"
+    style = Image.fromarray(synth.lidar_frame(80, 2))
+    contents = [Image.fromarray(synth.radar_frame(80, s)) for s in (1, 5, 9)]
+    single = [np.asarray(do_transfer_style(cfg, model, c, style, dev)) for c in contents]
+    batch = [np.asarray(o) for o in do_transfer_style_batch(cfg, model, contents, style, dev)]
+    assert len(batch) == 3
+    for a, b in zip(single, batch):
+        assert np.array_equal(a, b)

@@ -89,10 +89,13 @@ def test_feature_export_and_gram_targets(model_cfg, golden):
         assert abs(float(G.double().sum()) - g[f"gram{k}_sums_f64"][0]) <= 2e-5 * abs(g[f"gram{k}_sums_f64"][0])
 
 
-def test_closure_is_bitwise_deterministic_and_batch_consistent(model_cfg):
+@pytest.mark.parametrize("size", [64, 256])
+def test_closure_is_bitwise_deterministic_and_batch_consistent(model_cfg, size):
+    """256^2 is large enough for the conv kernels' stream-K split (several chunks per CTA, partial tiles exchanged between
+    CTAs, three frames per launch): the per-frame partition must make a batch round exactly like single frames."""
     cfg, model = model_cfg
-    content, style = frames(64, dev, "radar")
-    c2, _ = frames(64, dev, "radar", cseed=5)
+    content, style = frames(size, dev, "radar")
+    c2, _ = frames(size, dev, "radar", cseed=5)
     plan1 = prepare_plan(model, cfg, content, style)
     x1 = content + noise_like(content)
     l_a, g_a = plan1.loss_and_grad(x1)
@@ -103,9 +106,10 @@ def test_closure_is_bitwise_deterministic_and_batch_consistent(model_cfg):
     x2 = c2 + noise_like(c2, seed=4)
     l_c, g_c = plan_c2.loss_and_grad(x2)
     l_c, g_c = l_c.clone(), g_c.clone()
-    # a batch of two independent frames gives each frame exactly its single-frame result
-    both = torch.cat([content, c2])
+    # a batch of three independent frames gives each frame exactly its single-frame result
+    both = torch.cat([content, c2, content])
     planb = prepare_plan(model, cfg, both, style)
-    lb, gb = planb.loss_and_grad(torch.cat([x1, x2]))
+    lb, gb = planb.loss_and_grad(torch.cat([x1, x2, x1]))
     assert torch.equal(lb[0], l_a[0]) and torch.equal(gb[0], g_a[0])
     assert torch.equal(lb[1], l_c[0]) and torch.equal(gb[1], g_c[0])
+    assert torch.equal(lb[2], l_a[0]) and torch.equal(gb[2], g_a[0])
