@@ -311,6 +311,7 @@ def run_ours(args):
         roof = {"bound": "tensor", "kernel": dom[0], "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src + " bf16 sustained",
                 "launches_per_eval": n // 3, "share_of_closure": tms / total_ms,
+                "traffic_scope": "DRAM bytes (read + write) summed over the same launches of one closure, from the ncu capture under profiles/",
                 "note": "algorithmic FLOPs (2*M*N*K, single pass) of all conv_halo launches (13 forward + 13 data-gradient convs incl. the fused Gram backward) of one closure / their summed CUDA-event time; "
                         "the kernel issues 3 MMAs per product (hi/lo split), so tensor-pipe activity is ~3x this fraction"}
     else:
