@@ -150,64 +150,90 @@ __global__ void weight_repack_kernel(const float* __restrict__ w, int Cout, int 
 // First conv (Cin = 3, K = 27): HBM-bound, exact fp32 on CUDA cores. x is the reference's fp32 NCHW image
 // (the L-BFGS vector); output = relu planes. Reference: vgg.py:52 for conv1_1.
 // ------------------------------------------------------------------------------------------------------------
+// Register-tiled: a block owns a 32 x 8 pixel tile and stages its 34 x 10 x 3 input halo in shared memory; four threads share
+// a group of 4 consecutive pixels, thread q producing channels [8q, 8q+8) and [32+8q, 32+8q+8) for all four pixels (64
+// accumulators). Per (ci, ky) a thread reads 6 inputs and, per kx, 4 broadcast float4 of weights for 64 FMAs; the four
+// 16-byte stores of a pixel group form one contiguous 64-byte run per plane.
+constexpr int CFF_TX = 32, CFF_TY = 8, CFF_HX = 36 /* 34 padded */, CFF_HY = 10;
+
 template <int COUT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /*[COUT][3][3][3]*/,
                       const float* __restrict__ bias, uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo,
                       int NB, int H, int W, float out_scale) {
+    static_assert(COUT == 64, "channel split below is written for 64 output channels");
     __shared__ __align__(16) float ws[27][COUT];
+    __shared__ __align__(16) float sx[3][CFF_HY][CFF_HX];
     __shared__ float bs[COUT];
-    for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 27 * COUT; i += blockDim.x) {
         const int co = i / 27, t = i % 27;      // w index = co*27 + (ci*9 + ky*3 + kx)
         ws[t][co] = w[i];
     }
-    for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = bias[i];
-    __syncthreads();
+    for (int i = tid; i < COUT; i += blockDim.x) bs[i] = bias[i];
+    const int n = blockIdx.z;
+    const int x0 = blockIdx.x * CFF_TX, y0 = blockIdx.y * CFF_TY;
     const size_t HW = (size_t)H * W;
-    const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (gid >= (size_t)NB * HW) return;
-    const int n = (int)(gid / HW);
-    const int pix = (int)(gid % HW);
-    const int y = pix / W, xx = pix % W;
-    float in[27];
+    for (int i = tid; i < 3 * CFF_HY * 34; i += blockDim.x) {
+        const int ci = i / (CFF_HY * 34), r = i % (CFF_HY * 34), hy = r / 34, hx = r % 34;
+        const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+        sx[ci][hy][hx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(x + ((size_t)n * 3 + ci) * HW + (size_t)gy * W + gx) : 0.f;
+    }
+    __syncthreads();
+    const int q = tid & 3, pq = tid >> 2;
+    const int lx0 = (pq & 7) * 4, ly = pq >> 3;
+    float acc[4][16];
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+        for (int c = 0; c < 16; ++c) acc[i][c] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            // output (ly, lx) reads input halo row ly + ky, columns lx + kx  (halo origin = tile origin - 1)
+            const float* row = &sx[ci][ly + ky][lx0];
+            const float4 d0 = *reinterpret_cast<const float4*>(row);
+            const float2 d1 = *reinterpret_cast<const float2*>(row + 4);
+            const float d[6] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y};
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const int yy = y + ky - 1, xq = xx + kx - 1;
-                in[ci * 9 + ky * 3 + kx] =
-                    (yy >= 0 && yy < H && xq >= 0 && xq < W) ? __ldg(x + ((size_t)n * 3 + ci) * HW + (size_t)yy * W + xq) : 0.f;
+                const int t = ci * 9 + ky * 3 + kx;
+                float wv[16];
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+#pragma unroll
+                    for (int c = 0; c < 8; c += 4) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(&ws[t][g * 32 + q * 8 + c]);
+                        wv[g * 8 + c] = w4.x; wv[g * 8 + c + 1] = w4.y; wv[g * 8 + c + 2] = w4.z; wv[g * 8 + c + 3] = w4.w;
+                    }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) acc[i][c] = fmaf(d[i + kx], wv[c], acc[i][c]);
             }
-    float acc[COUT];
-#pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
-#pragma unroll
-    for (int t = 0; t < 27; ++t) {
-        const float xv = in[t];
-#pragma unroll
-        for (int c = 0; c < COUT; c += 4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(&ws[t][c]);
-            acc[c] = fmaf(xv, w4.x, acc[c]);
-            acc[c + 1] = fmaf(xv, w4.y, acc[c + 1]);
-            acc[c + 2] = fmaf(xv, w4.z, acc[c + 2]);
-            acc[c + 3] = fmaf(xv, w4.w, acc[c + 3]);
         }
     }
-    uint4* dh = reinterpret_cast<uint4*>(out_hi + gid * COUT);
-    uint4* dl = reinterpret_cast<uint4*>(out_lo + gid * COUT);
+    const int y = y0 + ly;
+    if (y >= H) return;
 #pragma unroll
-    for (int c = 0; c < COUT; c += 8) {
-        uint32_t h[4], l[4];
+    for (int i = 0; i < 4; ++i) {
+        const int xx = x0 + lx0 + i;
+        if (xx >= W) continue;
+        const size_t pix = ((size_t)n * H + y) * W + xx;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float a = fmaxf(acc[c + 2 * e] + bs[c + 2 * e], 0.f) * out_scale;
-            const float b = fmaxf(acc[c + 2 * e + 1] + bs[c + 2 * e + 1], 0.f) * out_scale;
-            split_pack<false>(a, b, h[e], l[e]);
+        for (int g = 0; g < 2; ++g) {
+            const int cb = g * 32 + q * 8;
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float a = fmaxf(acc[i][g * 8 + 2 * e] + bs[cb + 2 * e], 0.f) * out_scale;
+                const float b = fmaxf(acc[i][g * 8 + 2 * e + 1] + bs[cb + 2 * e + 1], 0.f) * out_scale;
+                split_pack<false>(a, b, h[e], l[e]);
+            }
+            *reinterpret_cast<uint4*>(out_hi + pix * COUT + cb) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(out_lo + pix * COUT + cb) = make_uint4(l[0], l[1], l[2], l[3]);
         }
-        dh[c >> 3] = make_uint4(h[0], h[1], h[2], h[3]);
-        dl[c >> 3] = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 

@@ -57,8 +57,7 @@ int ist_op_conv3x3_relu_fwd(const float* x, const float* w, const float* b, floa
     IST_TRY(t.alloc(&ol, (size_t)NB * HW * cout));
     if (cin == 3) {
         if (cout != 64) return fail(IST_ERR_ARG, "first-layer kernel is built for cout == 64");
-        const size_t px = (size_t)NB * HW;
-        conv_first_fwd_kernel<64><<<(unsigned)((px + 127) / 128), 128, 0, st>>>(x, w, b, oh, ol, NB, H, W, kS);
+        conv_first_fwd_kernel<64><<<dim3((W + CFF_TX - 1) / CFF_TX, (H + CFF_TY - 1) / CFF_TY, NB), 256, 0, st>>>(x, w, b, oh, ol, NB, H, W, kS);
         IST_CUDA(cudaGetLastError());
     } else {
         uint16_t *ih, *il, *fh, *fl, *dh, *dl;

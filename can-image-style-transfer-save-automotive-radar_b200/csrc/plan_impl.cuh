@@ -112,7 +112,7 @@ int run_forward(ist_plan* P, const float* x, int upto, cudaStream_t st, int from
             if (l == 0) {
                 const size_t px = (size_t)P->NB * L.H * L.W;
                 launch_pre("conv_first_fwd", 2.0 * px * 64 * 27, px * (12.0 + 256.0), st);
-                conv_first_fwd_kernel<64><<<(unsigned)((px + 127) / 128), 128, 0, st>>>(x, L.w_f32, L.bias, L.out.hi, L.out.lo,
+                conv_first_fwd_kernel<64><<<dim3((L.W + CFF_TX - 1) / CFF_TX, (L.H + CFF_TY - 1) / CFF_TY, P->NB), 256, 0, st>>>(x, L.w_f32, L.bias, L.out.hi, L.out.lo,
                                                                                      P->NB, L.H, L.W, kActScale);
                 launch_post(st);
                 IST_CUDA(cudaGetLastError());
