@@ -242,12 +242,14 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /
 // N = 3 output channels is no tensor-core shape, so this is a register-tiled CUDA-core kernel: a block owns a 32 x 16
 // pixel tile, stages the (34 x 18)-pixel halo of dY for 16 channels at a time in shared memory as fp32 (hi + lo summed
 // once instead of once per tap), and every thread produces 4 consecutive pixels x 3 channels, so that per (co, ky) it
-// issues 2 shared loads of dY and 3 broadcast loads of weights for 36 FMAs.
+// issues 2 shared loads of dY and 3 broadcast loads of weights for 36 FMAs. The 256 threads of a block form two halves that
+// take 8 of the 16 staged channels each (twice the warps per block for the same shared memory); the halves' sums are combined
+// through shared memory at the end, half 1 added to half 0 — a fixed order.
 constexpr int CFD_TX = 32, CFD_TY = 16, CFD_HX = 36 /* 34 padded to a multiple of 4 */, CFD_HY = 18, CFD_CO = 16;
 constexpr int CFD_SMEM = (CFD_CO * CFD_HY * CFD_HX + 64 * 9 * 4) * 4;
 
 template <int COUT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 conv_first_dgrad_kernel(const uint16_t* __restrict__ g_hi, const uint16_t* __restrict__ g_lo,
                         const float* __restrict__ w /*[COUT][3][3][3]*/, float* __restrict__ grad, int NB, int H, int W) {
     extern __shared__ __align__(16) float cfd_smem[];
@@ -260,7 +262,8 @@ conv_first_dgrad_kernel(const uint16_t* __restrict__ g_hi, const uint16_t* __res
     }
     const int n = blockIdx.z;
     const int x0 = blockIdx.x * CFD_TX, y0 = blockIdx.y * CFD_TY;
-    const int lx0 = (tid & 7) * 4, ly = tid >> 3;
+    const int half = tid >> 7, t7 = tid & 127;
+    const int lx0 = (t7 & 7) * 4, ly = t7 >> 3;
     float acc[4][3];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; }
@@ -290,7 +293,7 @@ conv_first_dgrad_kernel(const uint16_t* __restrict__ g_hi, const uint16_t* __res
         }
         __syncthreads();
 #pragma unroll 2
-        for (int c = 0; c < CFD_CO; ++c) {
+        for (int c = half * (CFD_CO / 2); c < (half + 1) * (CFD_CO / 2); ++c) {
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
                 // halo row of dY that tap ky of output row ly reads: (y - ky + 1) - (y0 - 1) = ly - ky + 2
@@ -312,6 +315,19 @@ conv_first_dgrad_kernel(const uint16_t* __restrict__ g_hi, const uint16_t* __res
             }
         }
     }
+    __syncthreads();                                   // the dY stage is free: reuse it to combine the two channel halves
+    if (half == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) sd[(i * 3 + ci) * 128 + t7] = acc[i][ci];
+    }
+    __syncthreads();
+    if (half == 1) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) acc[i][ci] += sd[(i * 3 + ci) * 128 + t7];
     const int y = y0 + ly, x = x0 + lx0;
     if (y >= H || x >= W) return;
     const size_t HW = (size_t)H * W;
@@ -383,7 +399,7 @@ __global__ void maxpool_fwd_kernel(const uint16_t* __restrict__ in_hi, const uin
 //          + addend(pos) (if any) + content_coef * (F - T)(pos) (if any);  then v = F > 0 ? v : 0 (if mask)
 // Output: bf16 planes (the dY the next dgrad consumes) or fp32 NHWC (when a style seed is still to be added).
 // Covers autograd of max_pool2d + relu (threshold_backward) and the content MSE seed (main.py:36-37).
-// One thread = one 2x2 window (ceil grid so odd edges are written too) x 8 channels.
+// One thread = one 2x2 window (ceil grid so odd edges are written too) x 4 channels.
 // ------------------------------------------------------------------------------------------------------------
 struct RouteParams {
     int NB, H, W, C;
@@ -400,47 +416,46 @@ struct RouteParams {
     float* out_f32;
 };
 
-__global__ void grad_route_kernel(const RouteParams p) {
-    const int Hc = (p.H + 1) >> 1, Wc = (p.W + 1) >> 1, C8 = p.C >> 3;
+// One thread = one 2x2 window x 4 channels (8-byte plane accesses, 16-byte fp32 accesses): half the registers of an
+// 8-channel thread, so four 256-thread blocks fit per SM and enough loads are in flight to stream at HBM speed.
+__global__ void __launch_bounds__(256, 4) grad_route_kernel(const RouteParams p) {
+    const int Hc = (p.H + 1) >> 1, Wc = (p.W + 1) >> 1, C4 = p.C >> 2;
     const int Ho = p.H >> 1, Wo = p.W >> 1;
-    const size_t total = (size_t)p.NB * Hc * Wc * C8;
+    const size_t total = (size_t)p.NB * Hc * Wc * C4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c8 = (int)(i % C8);
-        size_t r = i / C8;
+        const int c4 = (int)(i % C4);
+        size_t r = i / C4;
         const int xo = (int)(r % Wc);
         r /= Wc;
         const int yo = (int)(r % Hc);
         const int n = (int)(r / Hc);
         const bool window = (p.g_pool != nullptr) && (yo < Ho) && (xo < Wo);
-        float g[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) g[e] = 0.f;
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
         if (window) {
-            const float4* gp = reinterpret_cast<const float4*>(p.g_pool + ((((size_t)n * Ho + yo) * Wo + xo) * p.C) + c8 * 8);
-            const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
-            g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.g_pool + ((((size_t)n * Ho + yo) * Wo + xo) * p.C) + c4 * 4));
+            g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w;
         }
-        float fv[4][8];
+        float fv[4][4];
         bool inb[4];
+        size_t o4[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
             inb[k] = (yy < p.H) && (xx < p.W);
+            o4[k] = ((((size_t)n * p.H + (inb[k] ? yy : 0)) * p.W + (inb[k] ? xx : 0)) * p.C) / 4 + c4;
             if (inb[k]) {
-                const size_t o = ((((size_t)n * p.H + yy) * p.W + xx) * p.C) / 8 + c8;
-                const uint4 h = __ldg(reinterpret_cast<const uint4*>(p.f_hi) + o);
-                const uint4 l = __ldg(reinterpret_cast<const uint4*>(p.f_lo) + o);
-                const uint32_t uh[4] = {h.x, h.y, h.z, h.w}, ul[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) unpack_sum<false>(uh[e], ul[e], fv[k][2 * e], fv[k][2 * e + 1]);
+                const uint2 h = __ldg(reinterpret_cast<const uint2*>(p.f_hi) + o4[k]);
+                const uint2 l = __ldg(reinterpret_cast<const uint2*>(p.f_lo) + o4[k]);
+                unpack_sum<false>(h.x, l.x, fv[k][0], fv[k][1]);
+                unpack_sum<false>(h.y, l.y, fv[k][2], fv[k][3]);
             } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) fv[k][e] = 0.f;
+                for (int e = 0; e < 4; ++e) fv[k][e] = 0.f;
             }
         }
-        int arg[8];
+        int arg[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < 4; ++e) {
             int a = 0;
             float best = fv[0][e];
 #pragma unroll
@@ -451,44 +466,36 @@ __global__ void grad_route_kernel(const RouteParams p) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (!inb[k]) continue;
-            const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
-            const size_t o8 = ((((size_t)n * p.H + yy) * p.W + xx) * p.C) / 8 + c8;
-            float v[8];
+            float v[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = (window && arg[e] == k) ? g[e] : 0.f;
+            for (int e = 0; e < 4; ++e) v[e] = (window && arg[e] == k) ? g[e] : 0.f;
             if (p.addend != nullptr) {
-                const float4* ap = reinterpret_cast<const float4*>(p.addend) + o8 * 2;
-                const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
-                v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+                const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.addend) + o4[k]);
+                v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
             }
             if (p.t_hi != nullptr) {
-                const uint4 fh = __ldg(reinterpret_cast<const uint4*>(p.f_hi) + o8);
-                const uint4 fl = __ldg(reinterpret_cast<const uint4*>(p.f_lo) + o8);
-                const uint4 th = __ldg(reinterpret_cast<const uint4*>(p.t_hi) + o8);
-                const uint4 tl = __ldg(reinterpret_cast<const uint4*>(p.t_lo) + o8);
-                const uint32_t ua[4] = {fh.x, fh.y, fh.z, fh.w}, ub[4] = {fl.x, fl.y, fl.z, fl.w};
-                const uint32_t uc[4] = {th.x, th.y, th.z, th.w}, ud[4] = {tl.x, tl.y, tl.z, tl.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    v[2 * e] += p.content_coef * ((h_lo_f(ua[e]) - h_lo_f(uc[e])) + (h_lo_f(ub[e]) - h_lo_f(ud[e])));
-                    v[2 * e + 1] += p.content_coef * ((h_hi_f(ua[e]) - h_hi_f(uc[e])) + (h_hi_f(ub[e]) - h_hi_f(ud[e])));
-                }
+                const uint2 fh = __ldg(reinterpret_cast<const uint2*>(p.f_hi) + o4[k]);
+                const uint2 fl = __ldg(reinterpret_cast<const uint2*>(p.f_lo) + o4[k]);
+                const uint2 th = __ldg(reinterpret_cast<const uint2*>(p.t_hi) + o4[k]);
+                const uint2 tl = __ldg(reinterpret_cast<const uint2*>(p.t_lo) + o4[k]);
+                v[0] += p.content_coef * ((h_lo_f(fh.x) - h_lo_f(th.x)) + (h_lo_f(fl.x) - h_lo_f(tl.x)));
+                v[1] += p.content_coef * ((h_hi_f(fh.x) - h_hi_f(th.x)) + (h_hi_f(fl.x) - h_hi_f(tl.x)));
+                v[2] += p.content_coef * ((h_lo_f(fh.y) - h_lo_f(th.y)) + (h_lo_f(fl.y) - h_lo_f(tl.y)));
+                v[3] += p.content_coef * ((h_hi_f(fh.y) - h_hi_f(th.y)) + (h_hi_f(fl.y) - h_hi_f(tl.y)));
             }
             if (p.apply_mask) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
+                for (int e = 0; e < 4; ++e)
                     if (!(fv[k][e] > 0.f)) v[e] = 0.f;
             }
             if (p.out_f32 != nullptr) {
-                float4* d = reinterpret_cast<float4*>(p.out_f32) + o8 * 2;
-                d[0] = make_float4(v[0], v[1], v[2], v[3]);
-                d[1] = make_float4(v[4], v[5], v[6], v[7]);
+                reinterpret_cast<float4*>(p.out_f32)[o4[k]] = make_float4(v[0], v[1], v[2], v[3]);
             } else {
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) split_pack<true>(v[2 * e], v[2 * e + 1], h[e], l[e]);
-                reinterpret_cast<uint4*>(p.out_hi)[o8] = make_uint4(h[0], h[1], h[2], h[3]);
-                reinterpret_cast<uint4*>(p.out_lo)[o8] = make_uint4(l[0], l[1], l[2], l[3]);
+                uint32_t h0, l0, h1, l1;
+                split_pack<true>(v[0], v[1], h0, l0);
+                split_pack<true>(v[2], v[3], h1, l1);
+                reinterpret_cast<uint2*>(p.out_hi)[o4[k]] = make_uint2(h0, h1);
+                reinterpret_cast<uint2*>(p.out_lo)[o4[k]] = make_uint2(l0, l1);
             }
         }
     }

@@ -364,7 +364,7 @@ inline int launch_conv_first_dgrad(cudaStream_t st, const uint16_t* g_hi, const 
     const double px = (double)NB * H * W;
     launch_pre("conv_first_dgrad", 2.0 * px * 64 * 27, px * (12.0 + 256.0), st);
     dim3 grid((W + CFD_TX - 1) / CFD_TX, (H + CFD_TY - 1) / CFD_TY, NB);
-    conv_first_dgrad_kernel<64><<<grid, 128, CFD_SMEM, st>>>(g_hi, g_lo, w, grad, NB, H, W);
+    conv_first_dgrad_kernel<64><<<grid, 256, CFD_SMEM, st>>>(g_hi, g_lo, w, grad, NB, H, W);
     launch_post(st);
     IST_CUDA(cudaGetLastError());
     return IST_OK;

@@ -162,7 +162,7 @@ static int route_op(const float* feat, const float* g_pool_nchw, const float* ad
     memset(&r, 0, sizeof(r));
     r.NB = NB; r.H = H; r.W = W; r.C = C; r.g_pool = gp; r.f_hi = fh; r.f_lo = fl; r.addend = ad; r.apply_mask = mask;
     r.out_f32 = o32;
-    const size_t items = (size_t)NB * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+    const size_t items = (size_t)NB * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
     grad_route_kernel<<<ew_grid(items, 256), 256, 0, st>>>(r);
     IST_CUDA(cudaGetLastError());
     nhwc_to_nchw_f32_kernel<<<ew_grid((size_t)NB * H * W * C, 256), 256, 0, st>>>(o32, dx, NB, C, H * W);
@@ -308,7 +308,7 @@ int ist_op_mse(const float* x, const float* tg, float weight, float* loss, float
     r.NB = NB; r.H = H; r.W = W; r.C = C; r.f_hi = fh; r.f_lo = fl; r.t_hi = th; r.t_lo = tl;
     r.content_coef = (float)(2.0 * weight / ((double)C * HW * kS));
     r.apply_mask = 0; r.out_f32 = o32;
-    const size_t items = (size_t)NB * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+    const size_t items = (size_t)NB * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
     grad_route_kernel<<<ew_grid(items, 256), 256, 0, st>>>(r);
     IST_CUDA(cudaGetLastError());
     nhwc_to_nchw_f32_kernel<<<ew_grid(n, 256), 256, 0, st>>>(o32, dx, NB, C, HW);

@@ -237,7 +237,7 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         r.apply_mask = to_f32 ? 0 : 1;
         r.out_hi = L.dY.hi; r.out_lo = L.dY.lo;
         r.out_f32 = to_f32 ? f32_out : nullptr;
-        const size_t items = (size_t)NB * ((L.H + 1) / 2) * ((L.W + 1) / 2) * (L.C / 8);
+        const size_t items = (size_t)NB * ((L.H + 1) / 2) * ((L.W + 1) / 2) * (L.C / 4);
         IST_EW("grad_route", (double)L.out_elems * (4 + 4 + (g_pool != nullptr ? 1 : 0) + (addend != nullptr ? 4 : 0) + (content ? 8 : 0)), st,
                grad_route_kernel<<<ew_grid(items, 256), 256, 0, st>>>(r));
         return IST_OK;
