@@ -269,6 +269,17 @@ inline int promote_steps() {
     }
     return v;
 }
+// The data-gradient is linear in its operands (no ReLU / pool decisions depend on it), so the ~3e-8-per-MMA truncation of a
+// longer tensor-core chain only adds ~1e-6 relative error to the gradient: one chain per 64-channel chunk (9 taps = 36 MMAs)
+// instead of one per k-step saves most of the promotion drains. IST_B200_PROMOTE_BWD overrides.
+inline int promote_steps_bwd() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("IST_B200_PROMOTE_BWD");
+        v = (e != nullptr && atoi(e) > 0) ? atoi(e) : 9;
+    }
+    return v;
+}
 // Fills the tiling fields of p (NB,H,W,Cin,Cout,taps,passes,mode and epilogue pointers must be set) and launches.
 // Stream-K workspace of the conv_halo kernel: one fp32 partial tile + one flag per CTA. One instance per plan (kernels of a
 // plan run on one stream); the per-op entry points share a process-wide one. IST_B200_NO_STREAMK=1 disables the split.
@@ -312,7 +323,7 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
     p.tiles_y = (p.H + p.TH - 1) / p.TH;
     const int nt = conv_n_tile(p.Cout);
     p.tiles_n = p.Cout / nt;
-    if (p.promote < 1) p.promote = promote_steps();
+    if (p.promote < 1) p.promote = (p.mode == CONV_GRAD) ? promote_steps_bwd() : promote_steps();
     p.idesc = conv_idesc(fmt, nt);
     p.idesc2 = conv_idesc(0, nt);
     p.extra_chunks = 0;
