@@ -58,6 +58,7 @@ LAYER_MAXPOOL2X2 = 1
 
 _c_int_p = ctypes.POINTER(ctypes.c_int)
 _c_float_p = ctypes.POINTER(ctypes.c_float)
+_c_double_p = ctypes.POINTER(ctypes.c_double)
 _vp = ctypes.c_void_p
 
 # name -> (restype, argtypes); must list every symbol of include/ist_b200.h (tests/test_abi.py checks that)
@@ -86,6 +87,12 @@ SIGNATURES = {
     "ist_lbfgs_reset": (ctypes.c_int, [_vp, _vp]),
     "ist_lbfgs_step": (ctypes.c_int, [_vp, _vp, _c_int_p, _c_float_p, _vp]),
     "ist_lbfgs_last_losses": (ctypes.c_int, [_vp, _c_float_p]),
+    "ist_image_resize_target": (ctypes.c_int, [ctypes.c_int] * 3 + [_c_int_p, _c_int_p]),
+    "ist_image_post_u8": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 3 + [_c_double_p, _vp]),
+    "ist_image_prep_u8": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 3 + [_c_double_p, _vp]),
+    "ist_image_resize_u8": (ctypes.c_int, [_vp, _vp, _vp] + [ctypes.c_int] * 5 + [_vp]),
+    "ist_image_handoff_workspace": (ctypes.c_size_t, [ctypes.c_int] * 5),
+    "ist_image_handoff": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_size_t] + [ctypes.c_int] * 5 + [_c_double_p, _vp]),
     "ist_op_conv3x3_relu_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
     "ist_op_conv3x3_dgrad": (ctypes.c_int, [_vp, _vp, _vp] + [ctypes.c_int] * 6 + [_vp]),
     "ist_op_maxpool2x2_fwd": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 4 + [_vp]),

@@ -3,3 +3,4 @@
 #include "plan_impl.cuh"
 #include "ops_impl.cuh"
 #include "lbfgs_impl.cuh"
+#include "image_impl.cuh"

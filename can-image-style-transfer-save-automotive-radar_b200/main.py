@@ -67,10 +67,11 @@ def transfer_style_schedule(cfg, sizes, state_dict=None):
     style_image = Image.open(cfg.DATA.STYLE_IMG_PATH)
     cfg = cfg.clone()
     cfg.DATA.IMG_SIZE = sizes[0]
-    out_image = do_transfer_style(cfg, model, content_image, style_image, device)
+    out_image, x = do_transfer_style(cfg, model, content_image, style_image, device, return_tensor=True)
     for s in sizes[1:]:
         cfg.HRDATA.IMG_SIZE = s
-        out_image = do_hr_transfer_style(cfg, model, content_image, style_image, out_image, device)
+        # the previous stage's result stays on the device: 8-bit clamp + bilinear up-scaling + re-preprocessing as kernels
+        out_image, x = do_hr_transfer_style(cfg, model, content_image, style_image, x, device, return_tensor=True)
     return out_image
 
 

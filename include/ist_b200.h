@@ -110,6 +110,27 @@ int ist_lbfgs_step(ist_lbfgs* opt, float* x_dev, int* evals_out, float* loss_out
 /* per-frame losses of the most recent closure evaluation: [batch, n_losses+1] */
 int ist_lbfgs_last_losses(ist_lbfgs* opt, float* losses_host);
 
+/* image pre/post-processing on the device ------------------------------------------------------- */
+/* 8-bit images are RGB, HWC, [batch,H,W,3] uint8 on the device; network images fp32 NCHW [batch,3,H,W] in the reference's
+ * preprocessed space (BGR, mean-subtracted, x255). mean_bgr = cfg.DATA.IMAGENET_MEAN (IST/config/defaults.py:86) as 3 host
+ * doubles. Results are bit-identical to the reference's torchvision / PIL pipeline. */
+/* output size of transforms.Scale(size) (IST/data/image_transform.py:9): smaller edge -> size, aspect kept (truncated) */
+int ist_image_resize_target(int H, int W, int size, int* Hout, int* Wout);
+/* ImageTransform.post_preparation (IST/data/image_transform.py:16-31): x/255 + mean, BGR->RGB, clamp [0,1], ToPILImage */
+int ist_image_post_u8(const float* x_dev, uint8_t* rgb_dev, int batch, int H, int W, const double* mean_bgr, void* stream);
+/* ImageTransform.preparation after the resize (image_transform.py:10-13): ToTensor, RGB->BGR, Normalize, mul_(255) */
+int ist_image_prep_u8(const uint8_t* rgb_dev, float* x_dev, int batch, int H, int W, const double* mean_bgr, void* stream);
+/* transforms.Scale on a PIL image (image_transform.py:9) = Image.resize(BILINEAR): Pillow's two-pass 8-bit resampling.
+ * tmp_dev: scratch [batch,Hin,Wout,3] bytes, needed only when both axes change (may be NULL otherwise). */
+int ist_image_resize_u8(const uint8_t* in_dev, uint8_t* out_dev, uint8_t* tmp_dev, int batch, int Hin, int Win, int Hout,
+                        int Wout, void* stream);
+/* coarse-to-fine hand-off of the optimised image (IST/model/engine/hr_transfer_style.py:21-27: post_preparation of the
+ * low-resolution result, preparation at HRDATA.IMG_SIZE) without leaving the device: x_lo [batch,3,Hin,Win] ->
+ * x_hi [batch,3,Hout,Wout]; work_dev = ist_image_handoff_workspace(...) bytes of scratch. */
+size_t ist_image_handoff_workspace(int batch, int Hin, int Win, int Hout, int Wout);
+int ist_image_handoff(const float* x_lo_dev, float* x_hi_dev, uint8_t* work_dev, size_t work_bytes, int batch, int Hin,
+                      int Win, int Hout, int Wout, const double* mean_bgr, void* stream);
+
 /* per-op entry points for unit parity (fp32 NCHW in/out, temporaries allocated inside) ---------------------- */
 int ist_op_conv3x3_relu_fwd(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev, int batch,
                             int cin, int cout, int H, int W, int apply_relu, void* stream);
