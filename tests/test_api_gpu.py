@@ -114,6 +114,26 @@ def test_frame_functions_with_pil(model_cfg, tmp_path):
     assert np.asarray(hr).std() > 0
 
 
+def test_device_handoff_equals_pil_handoff(model_cfg, tmp_path):
+    """Coarse-to-fine with the previous stage's tensor kept on the device (8-bit clamp + bilinear resize + re-preprocessing
+    as kernels) gives the same images as the reference's route through a PIL image (hr_transfer_style.py:21-27)."""
+    cfg, model = model_cfg
+    cfg = cfg.clone()
+    cfg.DATA.IMG_SIZE = 48
+    cfg.HRDATA.IMG_SIZE = 96
+    cfg.LOSS.MAX_ITER = 20
+    cfg.HRLOSS.MAX_ITER = 20
+    cfg.OUTPUT.DIR = str(tmp_path) + "/"
+    content = Image.fromarray(synth.radar_frame(64, 3))
+    style = Image.fromarray(synth.lidar_frame(64, 2))
+    out, x = do_transfer_style(cfg, model, content, style, dev, return_tensor=True)
+    assert tuple(x.shape) == (1, 3, 48, 48) and x.is_cuda
+    hr_pil = do_hr_transfer_style(cfg, model, content, style, out, dev)
+    hr_dev, x_hr = do_hr_transfer_style(cfg, model, content, style, x, dev, return_tensor=True)
+    assert tuple(x_hr.shape) == (1, 3, 96, 96)
+    assert np.array_equal(np.asarray(hr_pil), np.asarray(hr_dev))
+
+
 def test_batched_frames_equal_per_frame_calls(model_cfg, tmp_path):
     """do_transfer_style_batch == one do_transfer_style per frame (independent problems; at this size every layer's work split
     is the same for 1 and 3 frames, so the kernels round identically — see DESIGN.md 3 for large images)."""
