@@ -150,6 +150,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
     }
 
+    pdl_trigger();       // the next kernel of the stream may be scheduled as SMs free up (it waits for this grid itself)
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA_hi);
         tma_prefetch_desc(&tmB_hi);
@@ -174,6 +175,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    // everything above (barriers, tensor memory, descriptor prefetch) may overlap the previous kernel's tail; global memory
+    // is touched only from here on
+    pdl_wait();
     if (dbg != nullptr && threadIdx.x == 0) dbg[1] = clock64();
 
     const int cchunks = p.Cin >> 6;

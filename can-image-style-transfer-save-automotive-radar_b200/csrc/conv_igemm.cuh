@@ -52,6 +52,7 @@ struct ConvParams {
     int use_tma_store;     // conv_halo, CONV_FWD: the fp16 planes leave through shared memory + TMA store (tmO_hi / tmO_lo)
     int dbg_flags;         // timing experiments only: 2 = skip the A loads, 4 = skip the B loads (results are then garbage)
     long long* dbg_times;  // optional [gridDim.x][8] clock64 stamps of the kernel phases (IST_B200_DBG_TIMES=1)
+    int pdl;               // host-side hint: launch as programmatically dependent on the previous kernel of the stream
     uint32_t idesc;
     int mode;
     float alpha;             // host multiplier on the accumulator

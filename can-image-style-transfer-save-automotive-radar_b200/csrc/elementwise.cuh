@@ -171,6 +171,8 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /
         ws[t][co] = w[i];
     }
     for (int i = tid; i < COUT; i += blockDim.x) bs[i] = bias[i];
+    pdl_trigger();
+    pdl_wait();          // the weights above are constants; the image is written by the previous kernel of the stream
     const int n = blockIdx.z;
     const int x0 = blockIdx.x * CFF_TX, y0 = blockIdx.y * CFF_TY;
     const size_t HW = (size_t)H * W;
@@ -260,6 +262,8 @@ conv_first_dgrad_kernel(const uint16_t* __restrict__ g_hi, const uint16_t* __res
         const int co = i / 9, tap = i % 9;
         ws[i] = make_float4(w[(co * 3 + 0) * 9 + tap], w[(co * 3 + 1) * 9 + tap], w[(co * 3 + 2) * 9 + tap], 0.f);
     }
+    pdl_trigger();
+    pdl_wait();          // weights are constants; the gradient planes come from the previous kernel
     const int n = blockIdx.z;
     const int x0 = blockIdx.x * CFD_TX, y0 = blockIdx.y * CFD_TY;
     const int half = tid >> 7, t7 = tid & 127;
@@ -353,6 +357,8 @@ __global__ void maxpool_fwd_kernel(const uint16_t* __restrict__ in_hi, const uin
                                    int C) {
     const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
     const size_t total = (size_t)NB * Ho * Wo * C8;
+    pdl_trigger();
+    pdl_wait();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c8 = (int)(i % C8);
         size_t r = i / C8;
@@ -422,6 +428,8 @@ __global__ void __launch_bounds__(256, 4) grad_route_kernel(const RouteParams p)
     const int Hc = (p.H + 1) >> 1, Wc = (p.W + 1) >> 1, C4 = p.C >> 2;
     const int Ho = p.H >> 1, Wo = p.W >> 1;
     const size_t total = (size_t)p.NB * Hc * Wc * C4;
+    pdl_trigger();
+    pdl_wait();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % C4);
         size_t r = i / C4;
@@ -516,6 +524,8 @@ content_partial_kernel(const uint16_t* __restrict__ f_hi, const uint16_t* __rest
     const uint4* c = reinterpret_cast<const uint4*>(t_hi) + (size_t)fr * n8_per_frame;
     const uint4* d = reinterpret_cast<const uint4*>(t_lo) + (size_t)fr * n8_per_frame;
     float s = 0.f;
+    pdl_trigger();
+    pdl_wait();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8_per_frame; i += (size_t)gridDim.x * blockDim.x) {
         const uint4 va = __ldg(a + i), vb = __ldg(b + i), vc = __ldg(c + i), vd = __ldg(d + i);
         const uint32_t ua[4] = {va.x, va.y, va.z, va.w}, ub[4] = {vb.x, vb.y, vb.z, vb.w};
@@ -566,6 +576,8 @@ gram_reduce_kernel(const GramFinalizeParams p) {
     const int fr = blockIdx.z, C = L.C;
     const size_t CC = (size_t)C * C;
     float s = 0.f, mx = 0.f;
+    pdl_trigger();
+    pdl_wait();
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < CC; e += (size_t)gridDim.x * blockDim.x) {
         float g = 0.f;
         for (int sp = 0; sp < L.splits; ++sp) g += L.partial[((size_t)fr * L.splits + sp) * CC + e];
@@ -597,6 +609,8 @@ gram_dmat_kernel(const GramFinalizeParams p) {
     const int fr = blockIdx.z, C = L.C;
     const size_t CC = (size_t)C * C;
     float mx = 0.f;
+    pdl_trigger();
+    pdl_wait();
     for (int b = 0; b < GRAM_FIN_BLOCKS; ++b) mx = fmaxf(mx, L.blk_max[(size_t)fr * GRAM_FIN_BLOCKS + b]);
     int e2 = 0;
     if (mx > 0.f && isfinite(mx)) e2 = 13 - ilogbf(mx);
@@ -630,6 +644,8 @@ struct LossTotalParams {
 };
 __global__ void loss_total_kernel(const LossTotalParams p) {
     const int fr = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (fr >= p.NB) return;
     float* L = p.losses + (size_t)fr * p.loss_stride;
     for (int k = 0; k < p.n_content; ++k) {

@@ -77,6 +77,7 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const int groups_b = p.n_tile >> 6;
     const int promote = p.promote < 1 ? 1 : p.promote;
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_hi);
         if (p.passes == 3) tma_prefetch_desc(&tm_lo);
@@ -96,6 +97,7 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    pdl_wait();          // setup above overlaps the previous kernel's tail; the feature planes are read from here on
 
     if (warp == 0) {
         if (lane == 0) {

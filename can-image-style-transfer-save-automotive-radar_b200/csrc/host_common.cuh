@@ -83,6 +83,35 @@ inline void launch_post(cudaStream_t st) {
     if (b.profiling && !b.capturing && !b.recs.empty()) cudaEventRecord(b.recs.back().e1, st);
 }
 
+// Kernel launch through cudaLaunchKernelEx. `pdl` marks the launch as programmatically dependent on the previous kernel of
+// the stream: the grid may be scheduled while that kernel drains, so its prologue (barrier init, tensor-memory allocation,
+// descriptor prefetch, launch latency) overlaps the predecessor's tail. Every kernel launched this way executes
+// griddepcontrol.wait (pdl_wait) before it reads or writes global memory. IST_B200_NO_PDL=1 turns the attribute off.
+// kernel classes for IST_B200_PDL_MASK (default 3: measured in profiles/r01_pdl_ab.log, the optimiser kernels lose with it): 1 = tensor-core kernels, 2 = elementwise kernels of the closure,
+// 4 = optimiser kernels
+enum { PDL_TENSOR = 1, PDL_EW = 2, PDL_OPT = 4 };
+inline int pdl_mask() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("IST_B200_NO_PDL");
+        const char* m = getenv("IST_B200_PDL_MASK");
+        v = (e != nullptr && atoi(e) == 1) ? 0 : (m != nullptr ? atoi(m) : 3);
+    }
+    return v;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl & pdl_mask()) != 0 ? 1 : 0;      // pdl: 0 / false = plain launch, else the kernel's PDL_* class
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 inline int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -238,7 +267,7 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
         IST_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(long long) * 8 * 1024, st));
         ConvParams q = p;
         q.dbg_times = dbuf;
-        conv_halo_kernel<N_TILE><<<grid, 224, HaloCfg<N_TILE>::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, q);
+        IST_CUDA(launch_k(conv_halo_kernel<N_TILE>, dim3(grid), dim3(224), HaloCfg<N_TILE>::SMEM_BYTES, st, 0, a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, q));
         IST_CUDA(cudaStreamSynchronize(st));
         std::vector<long long> h(8 * (size_t)grid);
         IST_CUDA(cudaMemcpy(h.data(), dbuf, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost));
@@ -254,9 +283,8 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
         launch_post(st);
         return IST_OK;
     }
-    conv_halo_kernel<N_TILE><<<grid, 224, HaloCfg<N_TILE>::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, p);
+    IST_CUDA(launch_k(conv_halo_kernel<N_TILE>, dim3(grid), dim3(224), HaloCfg<N_TILE>::SMEM_BYTES, st, p.pdl != 0 ? PDL_TENSOR : 0, a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, p));
     launch_post(st);
-    IST_CUDA(cudaGetLastError());
     return IST_OK;
 }
 inline int conv_n_tile(int cout) { return cout >= 128 ? 128 : 64; }
@@ -366,7 +394,7 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
 }
 
 inline int launch_conv_first_dgrad(cudaStream_t st, const uint16_t* g_hi, const uint16_t* g_lo, const float* w, float* grad, int NB,
-                                   int H, int W) {
+                                   int H, int W, bool pdl = false) {
     static bool attr_done = false;
     if (!attr_done) {
         IST_CUDA(cudaFuncSetAttribute(conv_first_dgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFD_SMEM));
@@ -375,9 +403,8 @@ inline int launch_conv_first_dgrad(cudaStream_t st, const uint16_t* g_hi, const 
     const double px = (double)NB * H * W;
     launch_pre("conv_first_dgrad", 2.0 * px * 64 * 27, px * (12.0 + 256.0), st);
     dim3 grid((W + CFD_TX - 1) / CFD_TX, (H + CFD_TY - 1) / CFD_TY, NB);
-    conv_first_dgrad_kernel<64><<<grid, 256, CFD_SMEM, st>>>(g_hi, g_lo, w, grad, NB, H, W);
+    IST_CUDA(launch_k(conv_first_dgrad_kernel<64>, grid, dim3(256), CFD_SMEM, st, pdl ? PDL_EW : 0, g_hi, g_lo, w, grad, NB, H, W));
     launch_post(st);
-    IST_CUDA(cudaGetLastError());
     return IST_OK;
 }
 
@@ -397,7 +424,7 @@ inline void gram_split_plan(int NB, int HW, int C, int* splits, int* chunks_per_
     *splits = (total_chunks + cps - 1) / cps;
 }
 inline int launch_gram(cudaStream_t st, const CUtensorMap& m_hi, const CUtensorMap& m_lo, int NB, int HW, int C,
-                       int splits, int chunks_per_split, float* partial, int passes) {
+                       int splits, int chunks_per_split, float* partial, int passes, bool pdl = false) {
     static bool attr_done = false;
     if (!attr_done) {
         IST_CUDA(cudaFuncSetAttribute(gram_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg::SMEM_BYTES));
@@ -417,9 +444,8 @@ inline int launch_gram(cudaStream_t st, const CUtensorMap& m_hi, const CUtensorM
     const int tri = p.tiles_c * (p.tiles_c + 1) / 2;
     dim3 grid(splits, tri, NB);
     launch_pre("gram_syrk", 2.0 * NB * (double)HW * C * C, 4.0 * NB * (double)HW * C + 4.0 * NB * splits * (double)C * C, st);
-    gram_syrk_kernel<<<grid, 192, GramCfg::SMEM_BYTES, st>>>(m_hi, m_lo, p);
+    IST_CUDA(launch_k(gram_syrk_kernel, grid, dim3(192), GramCfg::SMEM_BYTES, st, pdl ? PDL_TENSOR : 0, m_hi, m_lo, p));
     launch_post(st);
-    IST_CUDA(cudaGetLastError());
     return IST_OK;
 }
 
@@ -438,6 +464,15 @@ inline int ew_grid(size_t work_items, int block) {
         __VA_ARGS__;                                 \
         ::ist::launch_post(st);                      \
         IST_CUDA(cudaGetLastError());                \
+    } while (0)
+
+// same bookkeeping, launched through launch_k (programmatic dependent launch when `pdl`):
+// IST_EWK("name", bytes, stream, pdl, kernel, grid, block, smem, args...)
+#define IST_EWK(name, bytes, st, pdl, kernel, grid, block, smem, ...)                                   \
+    do {                                                                                                \
+        ::ist::launch_pre(name, 0.0, (double)(bytes), st);                                              \
+        IST_CUDA(::ist::launch_k(kernel, dim3(grid), dim3(block), smem, st, pdl, __VA_ARGS__));         \
+        ::ist::launch_post(st);                                                                         \
     } while (0)
 
 struct DevMem {

@@ -24,6 +24,7 @@ namespace ist {
 int plan_batch(const ist_plan* P);
 int plan_image_elems(const ist_plan* P);
 int plan_n_losses(const ist_plan* P);
+void plan_set_pdl_first(ist_plan* P, bool on);
 
 constexpr int LB_MAXH = 112;          // history_size must be < LB_MAXH (shared-memory budget of the solve kernel)
 constexpr int LB_WT = 512;            // elements per warp-tile (16 per lane)
@@ -113,6 +114,8 @@ lbfgs_dots_kernel(const LbParams P) {
     for (int i = lane; i < LB_PART; i += 32) wacc[warp][i] = 0.0;
     wacc[warp][5 * LB_MAXH + 6] = 0.0;
     __syncwarp();
+    pdl_trigger();
+    pdl_wait();          // the frame state, the gradient and the history are written by the previous kernels of the stream
     const bool skip = (P.it > 1 && !F.active);
     const int n = P.n;
     const size_t fo = (size_t)b * n;
@@ -196,6 +199,8 @@ __global__ void __launch_bounds__(256)
 lbfgs_reduce_kernel(const LbParams P) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    pdl_trigger();
+    pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         // clears the "iteration computed" marker and remembers the step size of the direction that led to the gradient being
         // processed (the solve replaces F.t with the step size of the new direction)
@@ -237,6 +242,8 @@ lbfgs_solve_kernel(const LbParams P) {
     __shared__ double red[LB_MAXH];
     __shared__ int sh_go, sh_h;
     const int b = blockIdx.x, tid = threadIdx.x, m = P.m;
+    pdl_trigger();
+    pdl_wait();
     LbFrame& F = P.frames[b];
     double* SYg = P.SY + (size_t)b * LB_MAXH * LB_MAXH;
     double* YYg = P.YY + (size_t)b * LB_MAXH * LB_MAXH;
@@ -398,6 +405,8 @@ lbfgs_update_kernel(const LbParams P) {
     __shared__ float s_cy[LB_MAXH], s_cs[LB_MAXH];
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const LbFrame& F = P.frames[b];
+    pdl_trigger();
+    pdl_wait();
     for (int i = threadIdx.x; i < F.nread; i += blockDim.x) { s_slot[i] = F.read_slot[i]; s_cy[i] = F.read_cy[i]; s_cs[i] = F.read_cs[i]; }
     __syncthreads();
     float dmax = 0.f;
@@ -491,13 +500,16 @@ inline int lbfgs_enqueue_step(ist_lbfgs* O, float* x, cudaStream_t st) {
     LbParams P = O->P;
     P.x = x;
     for (int it = 1; it <= P.max_iter; ++it) {
-        IST_TRY(ist_plan_loss_and_grad(O->plan, x, O->g, O->losses, (void*)st));
+        plan_set_pdl_first(O->plan, it > 1);      // the closure then follows lbfgs_update_kernel on the same stream
+        const int rc_closure = ist_plan_loss_and_grad(O->plan, x, O->g, O->losses, (void*)st);
+        plan_set_pdl_first(O->plan, false);
+        IST_TRY(rc_closure);
         P.it = it;
         const double vb = 4.0 * P.NB * (double)P.n;
-        IST_EW("lbfgs_dots", vb * (3 + 2.0 * P.m), st, lbfgs_dots_kernel<<<dim3(P.nblk, P.NB), 256, 0, st>>>(P));
-        IST_EW("lbfgs_reduce", 8.0 * P.NB * P.nblk * LB_PART, st, lbfgs_reduce_kernel<<<dim3((LB_PART + 7) / 8, P.NB), 256, 0, st>>>(P));
-        IST_EW("lbfgs_solve", 16.0 * P.m * P.m, st, lbfgs_solve_kernel<<<P.NB, LB_SOLVE_THREADS, lb_solve_smem(P.m), st>>>(P));
-        IST_EW("lbfgs_update", vb * (9 + 2.0 * P.m), st, lbfgs_update_kernel<<<dim3(P.nblk, P.NB), 256, 0, st>>>(P));
+        IST_EWK("lbfgs_dots", vb * (3 + 2.0 * P.m), st, PDL_OPT, lbfgs_dots_kernel, dim3(P.nblk, P.NB), 256, 0, P);
+        IST_EWK("lbfgs_reduce", 8.0 * P.NB * P.nblk * LB_PART, st, PDL_OPT, lbfgs_reduce_kernel, dim3((LB_PART + 7) / 8, P.NB), 256, 0, P);
+        IST_EWK("lbfgs_solve", 16.0 * P.m * P.m, st, PDL_OPT, lbfgs_solve_kernel, P.NB, LB_SOLVE_THREADS, lb_solve_smem(P.m), P);
+        IST_EWK("lbfgs_update", vb * (9 + 2.0 * P.m), st, PDL_OPT, lbfgs_update_kernel, dim3(P.nblk, P.NB), 256, 0, P);
     }
     return IST_OK;
 }

@@ -75,6 +75,9 @@ struct ist_plan {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     ConvWorkspace skw;             // stream-K partial tiles of the conv kernel
+    // the first kernel of a closure is launched as programmatically dependent only when the caller knows that the previous
+    // operation of the stream is one of this library's kernels (the optimiser loop); see host_common.cuh launch_k
+    bool pdl_first = false;
     ~ist_plan() {
         skw.release();
         if (ev_fork != nullptr) cudaEventDestroy(ev_fork);
@@ -112,10 +115,9 @@ int run_forward(ist_plan* P, const float* x, int upto, cudaStream_t st, int from
             if (l == 0) {
                 const size_t px = (size_t)P->NB * L.H * L.W;
                 launch_pre("conv_first_fwd", 2.0 * px * 64 * 27, px * (12.0 + 256.0), st);
-                conv_first_fwd_kernel<64><<<dim3((L.W + CFF_TX - 1) / CFF_TX, (L.H + CFF_TY - 1) / CFF_TY, P->NB), 256, 0, st>>>(x, L.w_f32, L.bias, L.out.hi, L.out.lo,
-                                                                                     P->NB, L.H, L.W, kActScale);
+                IST_CUDA(launch_k(conv_first_fwd_kernel<64>, dim3((L.W + CFF_TX - 1) / CFF_TX, (L.H + CFF_TY - 1) / CFF_TY, P->NB), dim3(256), 0, st,
+                                  P->pdl_first ? PDL_EW : 0, x, (const float*)L.w_f32, (const float*)L.bias, L.out.hi, L.out.lo, P->NB, L.H, L.W, kActScale));
                 launch_post(st);
-                IST_CUDA(cudaGetLastError());
             } else {
                 ConvParams p;
                 memset(&p, 0, sizeof(p));
@@ -126,13 +128,14 @@ int run_forward(ist_plan* P, const float* x, int upto, cudaStream_t st, int from
                 p.bias = L.bias;
                 p.out_scale = kActScale;
                 p.out_hi = L.out.hi; p.out_lo = L.out.lo;
+                p.pdl = 1;
                 IST_TRY(launch_conv(st, L.mA_hi, L.mA_lo, L.mBf_hi, L.mBf_lo, p, 0, &L.mO_hi, &L.mO_lo, nullptr, &P->skw));
             }
         } else {
             const Layer& I = P->layers[l - 1];
             const size_t items = (size_t)P->NB * L.H * L.W * (L.C / 8);
-            IST_EW("maxpool_fwd", 5.0 * L.out_elems * 4, st,
-                   maxpool_fwd_kernel<<<ew_grid(items, 256), 256, 0, st>>>(I.out.hi, I.out.lo, L.out.hi, L.out.lo, P->NB, I.H, I.W, I.C));
+            IST_EWK("maxpool_fwd", 5.0 * L.out_elems * 4, st, PDL_EW, maxpool_fwd_kernel, ew_grid(items, 256), 256, 0,
+                    (const uint16_t*)I.out.hi, (const uint16_t*)I.out.lo, L.out.hi, L.out.lo, P->NB, I.H, I.W, I.C);
         }
     }
     P->forwarded_upto = upto;
@@ -208,6 +211,7 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
     auto dgrad = [&](const Layer& Cj, ConvParams p, const Layer* dst, const GramFuse* gf = nullptr) -> int {
         p.NB = NB; p.H = Cj.H; p.W = Cj.W; p.Cin = Cj.cout; p.Cout = Cj.cin; p.taps = 9;
         p.passes = P->passes_bwd; p.mode = CONV_GRAD; p.alpha = 1.f;
+        p.pdl = 1;
         return launch_conv(st, Cj.mG_hi, Cj.mG_lo, Cj.mBd_hi, Cj.mBd_lo, p, 1, dst != nullptr ? &dst->mGo_hi : nullptr,
                            dst != nullptr ? &dst->mGo_lo : nullptr, gf, &P->skw);
     };
@@ -221,6 +225,7 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         if (content) set_content(L, &p.f_hi, &p.f_lo, &p.t_hi, &p.t_lo, &p.content_coef);
         p.mask_hi = L.out.hi;
         p.out_hi = L.dY.hi; p.out_lo = L.dY.lo;
+        p.pdl = 1;
         return launch_conv(st, L.mFeat_hi, L.mFeat_lo, L.mD_hi, L.mD_lo, p, 0, &L.mGo_hi, &L.mGo_lo, nullptr, &P->skw);
     };
     auto route = [&](Layer& L, const float* g_pool, const float* addend, bool content, bool to_f32, float* f32_out) -> int {
@@ -238,8 +243,8 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         r.out_hi = L.dY.hi; r.out_lo = L.dY.lo;
         r.out_f32 = to_f32 ? f32_out : nullptr;
         const size_t items = (size_t)NB * ((L.H + 1) / 2) * ((L.W + 1) / 2) * (L.C / 4);
-        IST_EW("grad_route", (double)L.out_elems * (4 + 4 + (g_pool != nullptr ? 1 : 0) + (addend != nullptr ? 4 : 0) + (content ? 8 : 0)), st,
-               grad_route_kernel<<<ew_grid(items, 256), 256, 0, st>>>(r));
+        IST_EWK("grad_route", (double)L.out_elems * (4 + 4 + (g_pool != nullptr ? 1 : 0) + (addend != nullptr ? 4 : 0) + (content ? 8 : 0)), st, PDL_EW,
+                grad_route_kernel, ew_grid(items, 256), 256, 0, r);
         return IST_OK;
     };
 
@@ -303,7 +308,7 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         }
     }
     Layer& L0 = P->layers[0];
-    IST_TRY(launch_conv_first_dgrad(st, L0.dY.hi, L0.dY.lo, L0.w_f32, grad, NB, L0.H, L0.W));
+    IST_TRY(launch_conv_first_dgrad(st, L0.dY.hi, L0.dY.lo, L0.w_f32, grad, NB, L0.H, L0.W, true));
     return IST_OK;
 }
 
@@ -345,7 +350,7 @@ int run_loss_finalize(ist_plan* P, float* losses_dev, cudaStream_t st) {
             db += (double)P->NB * gp.L[k].C * gp.L[k].C * 12.0;
         }
         IST_EW("gram_reduce", rb, st, gram_reduce_kernel<<<grid, 256, 0, st>>>(gp));
-        IST_EW("gram_dmat", db, st, gram_dmat_kernel<<<grid, 256, 0, st>>>(gp));
+        IST_EWK("gram_dmat", db, st, PDL_EW, gram_dmat_kernel, grid, 256, 0, gp);
     }
     LossTotalParams lt;
     memset(&lt, 0, sizeof(lt));
@@ -361,7 +366,7 @@ int run_loss_finalize(ist_plan* P, float* losses_dev, cudaStream_t st) {
         lt.c_scale[k] = (float)((double)L.content_w / ((double)L.C * L.H * L.W * kActScale * kActScale));
         lt.n_content++;
     }
-    IST_EW("loss_total", 64.0 * P->NB, st, loss_total_kernel<<<(P->NB + 63) / 64, 64, 0, st>>>(lt));
+    IST_EWK("loss_total", 64.0 * P->NB, st, PDL_EW, loss_total_kernel, (P->NB + 63) / 64, 64, 0, lt);
     return IST_OK;
 }
 
@@ -695,4 +700,5 @@ namespace ist {
 int plan_batch(const ist_plan* P) { return P->NB; }
 int plan_image_elems(const ist_plan* P) { return 3 * P->H * P->W; }
 int plan_n_losses(const ist_plan* P) { return P->n_style + P->n_content; }
+void plan_set_pdl_first(ist_plan* P, bool on) { P->pdl_first = on; }
 }  // namespace ist

@@ -12,6 +12,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (griddepcontrol): no-ops when the grid was launched without the attribute
+// ----------------------------------------------------------------------------------------------
+// blocks until every grid this one programmatically depends on has completed and its memory operations are visible
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// lets the dependent grid be scheduled as soon as every CTA of this grid has executed it (or exited)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
