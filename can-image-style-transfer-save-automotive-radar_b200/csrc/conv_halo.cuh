@@ -20,7 +20,11 @@
 
 namespace ist {
 
-template <int N_TILE>
+// PAIR: the kernel runs as clusters of two CTAs (tcgen05 cta_group::2). The pair works on two horizontally adjacent pixel
+// tiles (M = 256: rank r owns tile column 2 * pair_column + r) and the same N_TILE output channels; every CTA loads its own
+// halo box and HALF of the weight rows (N_TILE / 2), the leader (rank 0) issues all MMAs, every CTA drains / stores its own
+// 128 accumulator rows. See ptx.cuh ("CTA pair") for the measured reason.
+template <int N_TILE, bool PAIR = false>
 struct HaloCfg {
     static constexpr int TW = 8, TH = 16, PW = TW + 2, PH = TH + 2;
     static constexpr int HALO_BYTES = PW * PH * 128;               // 23040
@@ -28,13 +32,22 @@ struct HaloCfg {
     static constexpr int A_PLANE = 23 * 1024;                      // 23552 >= HALO_BYTES, keeps every plane 1024-aligned
     static constexpr int A_STAGE = 2 * A_PLANE;
     static constexpr int A_STAGES = 2;
-    static constexpr int B_PLANE = N_TILE * 128;
+    static constexpr int B_ROWS = PAIR ? N_TILE / 2 : N_TILE;      // weight rows this CTA holds per tap
+    static constexpr int B_PLANE = B_ROWS * 128;
     static constexpr int B_STAGE = 2 * B_PLANE;
-    static constexpr int B_STAGES = (N_TILE == 128) ? 3 : 4;
-    static constexpr int TMEM_COLS = (4 * N_TILE < 32) ? 32 : 4 * N_TILE;
+    static constexpr int B_STAGES = PAIR ? ((N_TILE == 128) ? 6 : 8) : ((N_TILE == 128) ? 3 : 4);
+    // tensor-memory accumulators (N_TILE fp32 columns each, 512 columns in all):
+    //   N_TILE = 128: [main 0][main 1][main 2 | Gram][cross]      (third main buffer when no Gram k-steps are fused)
+    //   N_TILE =  64: [main 0..3][cross 0][cross 1][Gram 0][Gram 1]   (the Gram accumulator follows the cross buffer's parity)
+    // The cross buffer is read once per tile, so one is enough when the tiles are long; the main ring depth is what hides
+    // the promotion round trip (commit -> drain in both CTAs of a pair -> arrival at the leader) behind the next chains.
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int CROSS_COL = (N_TILE == 128) ? 3 * N_TILE : 4 * N_TILE;
+    static constexpr int GRAM_COL = (N_TILE == 128) ? 2 * N_TILE : 6 * N_TILE;
+    static constexpr bool XSINGLE = (N_TILE == 128);
     static constexpr int OUT_PLANE = 128 * 128;                    // output staging: 128 pixels x 64 channels x 2 B per plane
     static constexpr int OUT_BYTES = 2 * OUT_PLANE;                // hi + lo
-    static constexpr int SMEM_BYTES = A_STAGES * A_STAGE + B_STAGES * B_STAGE + OUT_BYTES + 256 + 1024;
+    static constexpr int SMEM_BYTES = A_STAGES * A_STAGE + B_STAGES * B_STAGE + OUT_BYTES + 512 + 1024;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_bo(uint32_t smem_addr, uint32_t sbo, uint32_t use_base_offset) {
@@ -112,7 +125,7 @@ __device__ __forceinline__ void conv_grad_regs_32(const ConvParams& p, float (&v
     }
 }
 
-template <int N_TILE>
+template <int N_TILE, bool PAIR>
 __global__ void __launch_bounds__(224, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -120,26 +133,41 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                  const __grid_constant__ CUtensorMap tmF_hi, const __grid_constant__ CUtensorMap tmF_lo,
                  const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CUtensorMap tmD_lo,
                  const ConvParams p) {
-    using Cfg = HaloCfg<N_TILE>;
+    using Cfg = HaloCfg<N_TILE, PAIR>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = smem_base;
     const uint32_t b_base = smem_base + Cfg::A_STAGES * Cfg::A_STAGE;
     const uint32_t o_base = b_base + Cfg::B_STAGES * Cfg::B_STAGE;      // output staging (1024-aligned planes)
     const uint32_t bar_base = o_base + Cfg::OUT_BYTES;
-    // barriers (8 B each): a_full[3] @0, a_empty[3] @24, b_full[4] @48, b_empty[4] @80, main_full[2] @112,
-    // main_empty[2] @128, cross_full[2] @144, cross_empty[2] @160, tmem base address @192
+    // barriers (8 B each): a_full[3] @0, a_empty[3] @24, b_full[8] @48, b_empty[8] @112, main_full[4] @176,
+    // main_empty[4] @208, cross_full[2] @240, cross_empty[2] @256, tmem base address @272
     auto afull = [&](int s) { return bar_base + 8u * s; };
     auto aempty = [&](int s) { return bar_base + 24u + 8u * s; };
     auto bfull = [&](int s) { return bar_base + 48u + 8u * s; };
-    auto bempty = [&](int s) { return bar_base + 80u + 8u * s; };
-    auto mfull = [&](uint32_t b) { return bar_base + 112u + 8u * b; };
-    auto mempty = [&](uint32_t b) { return bar_base + 128u + 8u * b; };
-    auto xfull = [&](uint32_t a) { return bar_base + 144u + 8u * a; };
-    auto xempty = [&](uint32_t a) { return bar_base + 160u + 8u * a; };
-    const uint32_t tmem_slot = bar_base + 192u;
+    auto bempty = [&](int s) { return bar_base + 112u + 8u * s; };
+    auto mfull = [&](uint32_t b) { return bar_base + 176u + 8u * b; };
+    auto mempty = [&](uint32_t b) { return bar_base + 208u + 8u * b; };
+    auto xfull = [&](uint32_t a) { return bar_base + 240u + 8u * a; };
+    auto xempty = [&](uint32_t a) { return bar_base + 256u + 8u * a; };
+    const uint32_t tmem_slot = bar_base + 272u;
     volatile uint32_t* tmem_slot_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 192);
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 272);
+    // CTA pair: rank 0 leads (issues the MMAs, owns the operand-full and accumulator-empty barriers both CTAs signal)
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    // barrier operations that differ between the two modes
+    auto commit = [&](uint32_t bar) {                 // arrive (in both CTAs of a pair) when this thread's MMAs have completed
+        if constexpr (PAIR) umma_pair_commit(bar, 3); else umma_commit(bar);
+    };
+    auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+        if constexpr (PAIR) umma_pair_f16_lh(d, a_lo, a_hi, b_lo, b_hi, idesc, acc); else umma_f16_lh(d, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+    };
+    auto arrive_leader = [&](uint32_t bar) {          // accumulator-drained arrivals go to the leader's barrier
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(bar, 0)); else mbar_arrive(bar);
+    };
+    auto arrive_both = [&](uint32_t bar) {            // plain arrival on this barrier in every CTA of the pair
+        if constexpr (PAIR) { mbar_arrive_cluster(mapa_u32(bar, 0)); mbar_arrive_cluster(mapa_u32(bar, 1)); } else mbar_arrive(bar);
+    };
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -162,17 +190,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const uint32_t releasers = (p.passes == 3) ? 2u : 1u;
         for (int s = 0; s < Cfg::A_STAGES; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), releasers); }
         for (int s = 0; s < Cfg::B_STAGES; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), releasers); }
-        for (uint32_t a = 0; a < 2; ++a) {
+        for (uint32_t a = 0; a < 4; ++a) {
             mbar_init(mfull(a), 1);
-            mbar_init(mempty(a), 128);
+            mbar_init(mempty(a), PAIR ? 8 : 4);           // one arrival per epilogue warp (of both CTAs of a pair)
+        }
+        for (uint32_t a = 0; a < 2; ++a) {
             mbar_init(xfull(a), 1);
-            mbar_init(xempty(a), 128);
+            mbar_init(xempty(a), PAIR ? 8 : 4);
         }
         fence_barrier_init();
     }
-    if (warp == 1) { tmem_alloc<Cfg::TMEM_COLS>(tmem_slot); }
+    if (warp == 1) {
+        if constexpr (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot); else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();      // the peer's barriers are initialised, too
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
     // everything above (barriers, tensor memory, descriptor prefetch) may overlap the previous kernel's tail; global memory
@@ -192,10 +224,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const bool split = (p.passes == 3);
     const bool halo = (taps == 9);
     const int planes = split ? 2 : 1;
-    const uint32_t a_tx = (uint32_t)(planes * (halo ? Cfg::HALO_BYTES : Cfg::EXACT_BYTES));
-    const uint32_t b_tx = (uint32_t)(planes * Cfg::B_PLANE);
+    // bytes counted on the (leader's) operand-full barriers: both CTAs of a pair load the same amounts
+    const uint32_t a_tx = (uint32_t)((PAIR ? 2 : 1) * planes * (halo ? Cfg::HALO_BYTES : Cfg::EXACT_BYTES));
+    const uint32_t b_tx = (uint32_t)((PAIR ? 2 : 1) * planes * Cfg::B_PLANE);
     const uint32_t a_sbo = halo ? (uint32_t)(Cfg::PW * 128) : 1024u;
-    const bool xsingle = xchunks > 0;             // single cross buffer when the second one holds the Gram accumulator
+    constexpr bool xsingle = Cfg::XSINGLE;
+    const uint32_t nmain = (N_TILE == 128) ? (xchunks > 0 ? 2u : 3u) : 4u;       // main accumulation ring (see HaloCfg)
 
     // Work distribution ("stream-K" over 64-channel chunks), frame by frame. A tile is CH = cchunks + xchunks chunk units; the
     // Gf = tiles_per_frame * CH units of ONE frame are cut into `cpf` equal contiguous ranges (cpf = CTAs per frame, chosen by
@@ -211,9 +245,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int CH = cchunks + xchunks;
     const int tiles_xy = p.tiles_y * p.tiles_x;
     const int tiles_f = tiles_xy * p.tiles_n;          // tiles of one frame
-    const int cpf = p.sk_cpf;
-    const int nfg = gridDim.x / cpf;                   // frame groups
-    const int fgroup = blockIdx.x / cpf, lid = blockIdx.x - fgroup * cpf;
+    // a CTA pair is ONE worker: tiles are pair tiles (p.tiles_x counts pair columns), ranges are per pair, and the partial
+    // tiles of rank r are exchanged between the rank-r CTAs of the pairs
+    const int cpf = p.sk_cpf;                          // workers per frame
+    const int wid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int nfg = nworkers / cpf;                    // frame groups
+    const int fgroup = wid / cpf, lid = wid - fgroup * cpf;
     int g_begin, g_end;                                // the host guarantees tiles_f * CH < 2^31
     if (p.sk_ws != nullptr) {
         const long long G = (long long)tiles_f * CH;
@@ -223,7 +261,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         g_begin = (int)((long long)tiles_f * lid / cpf) * CH;
         g_end = (int)((long long)tiles_f * (lid + 1) / cpf) * CH;
     }
-    if (blockIdx.x >= nfg * cpf) g_end = g_begin;      // surplus CTAs (grid not a multiple of cpf) have no work
+    if (wid >= nfg * cpf) g_end = g_begin;             // surplus workers (grid not a multiple of cpf) have no work
 #define IST_FOR_SEGMENTS(fr, fcount, tile, cbeg, cend)                                                          \
     for (int fr = fgroup, fcount = 0; fr < p.NB; fr += nfg, ++fcount)                                            \
         for (int g_ = g_begin, len_ = 0; g_ < g_end; g_ += len_)                                                 \
@@ -242,13 +280,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 const int tm = tile - tn * tiles_xy;
                 const int ty = tm / p.tiles_x;
                 const int tx = tm - ty * p.tiles_x;
-                const int x0 = tx * Cfg::TW - (halo ? 1 : 0), y0 = ty * Cfg::TH - (halo ? 1 : 0), n0 = tn * N_TILE;
+                const int x0 = (PAIR ? 2 * tx + (int)rank : tx) * Cfg::TW - (halo ? 1 : 0), y0 = ty * Cfg::TH - (halo ? 1 : 0);
+                const int n0 = tn * N_TILE + (int)rank * Cfg::B_ROWS;        // this CTA's half of the weight rows
                 for (int cc = cbeg; cc < cend; ++cc) {
                     const bool ex = cc >= cchunks;
                     const int c64 = (ex ? cc - cchunks : cc) * 64;
                     mbar_wait(aempty(as), aph ^ 1u);
                     const uint32_t sA = a_base + as * Cfg::A_STAGE;
-                    if (p.dbg_flags & 2) { mbar_arrive(afull(as)); } else {
+                    if constexpr (PAIR) {
+                        // the leader announces the bytes of both CTAs; each CTA's loads complete on the leader's barrier
+                        const uint32_t lbar = mapa_u32(afull(as), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(afull(as), a_tx);
+                        tma_load_4d_pair(sA, ex ? &tmF_hi : &tmA_hi, lbar, c64, x0, y0, fr);
+                        if (split) tma_load_4d_pair(sA + Cfg::A_PLANE, ex ? &tmF_lo : &tmA_lo, lbar, c64, x0, y0, fr);
+                    } else if (p.dbg_flags & 2) { mbar_arrive(afull(as)); } else {
                     mbar_arrive_expect_tx(afull(as), a_tx);
                     tma_load_4d(sA, ex ? &tmF_hi : &tmA_hi, afull(as), c64, x0, y0, fr);
                     if (split) tma_load_4d(sA + Cfg::A_PLANE, ex ? &tmF_lo : &tmA_lo, afull(as), c64, x0, y0, fr);
@@ -259,7 +304,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         const int bz = (p.b_frame || ex) ? fr : tap;
                         mbar_wait(bempty(bs), bph ^ 1u);
                         const uint32_t sB = b_base + bs * Cfg::B_STAGE;
-                        if (p.dbg_flags & 4) { mbar_arrive(bfull(bs)); } else {
+                        if constexpr (PAIR) {
+                            const uint32_t lbar = mapa_u32(bfull(bs), 0);
+                            if (rank == 0) mbar_arrive_expect_tx(bfull(bs), b_tx);
+                            tma_load_3d_pair(sB, ex ? &tmD_hi : &tmB_hi, lbar, c64, n0, bz);
+                            if (split) tma_load_3d_pair(sB + Cfg::B_PLANE, ex ? &tmD_lo : &tmB_lo, lbar, c64, n0, bz);
+                        } else if (p.dbg_flags & 4) { mbar_arrive(bfull(bs)); } else {
                         mbar_arrive_expect_tx(bfull(bs), b_tx);
                         tma_load_3d(sB, ex ? &tmD_hi : &tmB_hi, bfull(bs), c64, n0, bz);
                         if (split) tma_load_3d(sB + Cfg::B_PLANE, ex ? &tmD_lo : &tmB_lo, bfull(bs), c64, n0, bz);
@@ -270,6 +320,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
         }
     } else if (warp == 1) {
+      if (rank == 0) {
         // ------------------------------------------ MMA issuer 1: hi*hi chains ------------------------------------------
         // Two warps issue MMAs (this one the short hi*hi chains, warp 6 the hi*lo + lo*hi cross terms): a single issuing
         // thread sustains about one tcgen05.mma per ~107 cycles (measured, tools/probes/umma_probe.cu), above the 64-cycle
@@ -282,7 +333,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int kyn = halo ? 3 : 1;
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
-        uint32_t mcount = 0;
+        uint32_t mb = 0, mph = 0;                  // main ring position and phase
         bool first = true;
         IST_FOR_SEGMENTS(fr, fcount, tile, cbeg, cend) {
             (void)tile; (void)fr; (void)fcount;
@@ -296,9 +347,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     for (int kx = 0; kx < kyn; ++kx, ++kit) {
                         const bool last_tap = (ky == kyn - 1 && kx == kyn - 1);
                         const int in_chain = kit % promote;
-                        const uint32_t mb = mcount & 1u;
                         const bool chain_end = (in_chain == promote - 1) || (kit == kit_seg - 1);
-                        if (in_chain == 0) mbar_wait(mempty(mb), ((mcount >> 1) & 1u) ^ 1u);
+                        if (in_chain == 0) mbar_wait(mempty(mb), mph ^ 1u);
                         mbar_wait(bfull(bs), bph);
                         tc_fence_after();
                         if (elect_one()) {
@@ -308,15 +358,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                             const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4)
-                                umma_f16_lh(d_main, a_lo + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, (in_chain | k4) != 0 ? 1u : 0u);
-                            if (chain_end) umma_commit(mfull(mb));
-                            umma_commit(bempty(bs));
-                            if (last_tap) umma_commit(aempty(as));
+                                mma(d_main, a_lo + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, (in_chain | k4) != 0 ? 1u : 0u);
+                            if (chain_end) commit(mfull(mb));
+                            commit(bempty(bs));
+                            if (last_tap) commit(aempty(as));
                             if (dbg != nullptr) dbg[3] = clock64();
                         }
                         __syncwarp();
                         first = false;
-                        if (chain_end) ++mcount;
+                        if (chain_end && ++mb == nmain) { mb = 0; mph ^= 1u; }
                         if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                     }
                 }
@@ -328,17 +378,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 mbar_wait(afull(as), aph);
                 mbar_wait(bfull(bs), bph);
                 if (elect_one()) {
-                    mbar_arrive(bempty(bs));
-                    mbar_arrive(aempty(as));
+                    arrive_both(bempty(bs));
+                    arrive_both(aempty(as));
                 }
                 __syncwarp();
                 if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                 if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
             }
         }
+      }
     } else if (warp == 6) {
         // ------------------------------ MMA issuer 2: hi*lo + lo*hi cross terms, fused Gram k-steps ----------------------
-        if (split) {
+        if (split && rank == 0) {
             const uint32_t a_hi_w = ((a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
             const uint32_t b_hi_w = (1024u >> 4) | (1u << 14) | (2u << 29);
             const uint32_t idesc = p.idesc;
@@ -351,8 +402,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 (void)tile; (void)fr; (void)fcount;
                 const uint32_t xa = xsingle ? 0u : (scount & 1u);
                 const uint32_t xph = xsingle ? (scount & 1u) : ((scount >> 1) & 1u);
-                const uint32_t d_cross = tmem_base + (uint32_t)(2 * N_TILE) + xa * N_TILE;
-                const uint32_t d_gram = tmem_base + (uint32_t)(3 * N_TILE);
+                const uint32_t d_cross = tmem_base + (uint32_t)Cfg::CROSS_COL + xa * N_TILE;
+                const uint32_t d_gram = tmem_base + (uint32_t)Cfg::GRAM_COL + xa * N_TILE;
                 mbar_wait(xempty(xa), xph ^ 1u);
                 tc_fence_after();
                 int kit = 0, xc = 0;
@@ -372,13 +423,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                                     const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
 #pragma unroll
                                     for (int k4 = 0; k4 < 4; ++k4) {
-                                        umma_f16_lh(d_cross, a_lo + 2 * k4, a_hi_w, b_lo + (Cfg::B_PLANE >> 4) + 2 * k4, b_hi_w, idesc,
-                                                    (kit | k4) != 0 ? 1u : 0u);
-                                        umma_f16_lh(d_cross, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, 1u);
+                                        mma(d_cross, a_lo + 2 * k4, a_hi_w, b_lo + (Cfg::B_PLANE >> 4) + 2 * k4, b_hi_w, idesc,
+                                            (kit | k4) != 0 ? 1u : 0u);
+                                        mma(d_cross, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, 1u);
                                     }
-                                    umma_commit(bempty(bs));
-                                    if (last_tap) umma_commit(aempty(as));
-                                    if (last_tap && last_chunk) umma_commit(xfull(xa));
+                                    commit(bempty(bs));
+                                    if (last_tap) commit(aempty(as));
+                                    if (last_tap && last_chunk) commit(xfull(xa));
                                 }
                                 __syncwarp();
                                 if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
@@ -392,13 +443,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                             const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4) {
-                                umma_f16_lh(d_gram, a_lo + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc2, (xc | k4) != 0 ? 1u : 0u);
-                                umma_f16_lh(d_gram, a_lo + 2 * k4, a_hi_w, b_lo + (Cfg::B_PLANE >> 4) + 2 * k4, b_hi_w, idesc2, 1u);
-                                umma_f16_lh(d_gram, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc2, 1u);
+                                mma(d_gram, a_lo + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc2, (xc | k4) != 0 ? 1u : 0u);
+                                mma(d_gram, a_lo + 2 * k4, a_hi_w, b_lo + (Cfg::B_PLANE >> 4) + 2 * k4, b_hi_w, idesc2, 1u);
+                                mma(d_gram, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc2, 1u);
                             }
-                            umma_commit(bempty(bs));
-                            umma_commit(aempty(as));
-                            if (last_chunk) umma_commit(xfull(xa));
+                            commit(bempty(bs));
+                            commit(aempty(as));
+                            if (last_chunk) commit(xfull(xa));
                         }
                         __syncwarp();
                         ++xc;
@@ -414,7 +465,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int quad = warp & 3;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
         const int m = quad * 32 + lane;                  // accumulator row == pixel inside the tile
-        uint32_t mcount = 0, scount = 0;
+        uint32_t mb = 0, mph = 0, scount = 0;
         IST_FOR_SEGMENTS(fr, fcount, tile, cbeg, cend) {
             const int mend = cend < cchunks ? cend : cchunks;
             const int kit_seg = (mend > cbeg ? mend - cbeg : 0) * taps;
@@ -423,9 +474,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             float acc[N_TILE];
 #pragma unroll
             for (int j = 0; j < N_TILE; ++j) acc[j] = 0.f;
-            for (int ch = 0; ch < nchains; ++ch, ++mcount) {
-                const uint32_t mb = mcount & 1u;
-                mbar_wait(mfull(mb), (mcount >> 1) & 1u);
+            for (int ch = 0; ch < nchains; ++ch) {
+                mbar_wait(mfull(mb), mph);
                 tc_fence_after();
 #pragma unroll
                 for (int c0 = 0; c0 < N_TILE; c0 += 32) {
@@ -436,12 +486,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
                 }
                 tc_fence_before();
-                mbar_arrive(mempty(mb));
+                __syncwarp();
+                if (lane == 0) arrive_leader(mempty(mb));      // tcgen05.wait::ld is warp-wide: every lane's reads are done
+                if (++mb == nmain) { mb = 0; mph ^= 1u; }
             }
             const int tn = tile / tiles_xy;
             const int tm = tile - tn * tiles_xy;
             const int ty = tm / p.tiles_x;
-            const int tx = tm - ty * p.tiles_x;
+            const int tx = PAIR ? 2 * (tm - ty * p.tiles_x) + (int)rank : tm - ty * p.tiles_x;      // this CTA's pixel-tile column
             const int n0 = tn * N_TILE;
             if (split) {
                 const uint32_t xa = xsingle ? 0u : (scount & 1u);
@@ -451,7 +503,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
                     for (int c0 = 0; c0 < N_TILE; c0 += 32) {
                         uint32_t r[32];
-                        tmem_ld_32x32(lane_base + (uint32_t)(2 * N_TILE) + xa * N_TILE + c0, r);
+                        tmem_ld_32x32(lane_base + (uint32_t)Cfg::CROSS_COL + xa * N_TILE + c0, r);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
@@ -463,14 +515,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
                     for (int c0 = 0; c0 < N_TILE; c0 += 32) {
                         uint32_t r[32];
-                        tmem_ld_32x32(lane_base + (uint32_t)(3 * N_TILE) + c0, r);
+                        tmem_ld_32x32(lane_base + (uint32_t)Cfg::GRAM_COL + xa * N_TILE + c0, r);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc[c0 + j] = fmaf(a2, __uint_as_float(r[j]), acc[c0 + j]);
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(xempty(xa));
+                __syncwarp();
+                if (lane == 0) arrive_leader(xempty(xa));
             }
             ++scount;
             if (dbg != nullptr && threadIdx.x == 64) dbg[4] = clock64();
@@ -505,7 +558,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     const long long Gt = (long long)tiles_f * CH;
                     const int ob = (int)(Gt * ol / cpf), oe = (int)(Gt * (ol + 1) / cpf);
                     const int olen = (oe - ob) < (CH - covered) ? (oe - ob) : (CH - covered);
-                    const int oc = fgroup * cpf + ol;
+                    const int oc = PAIR ? 2 * (fgroup * cpf + ol) + (int)rank : fgroup * cpf + ol;      // same-rank CTA of worker ol
                     int* flag = p.sk_flags + 2 * oc + slot;
                     if (threadIdx.x == 64) {
                         int v = 0;
@@ -583,7 +636,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #undef IST_FOR_SEGMENTS
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();      // the peer's MMAs read this CTA's shared memory
     if (dbg != nullptr && threadIdx.x == 0) {
         dbg[6] = clock64();
         unsigned long long gt1;
@@ -592,7 +645,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+        if constexpr (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base); else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
 }
 

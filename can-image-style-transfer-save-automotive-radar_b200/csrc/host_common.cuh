@@ -99,17 +99,32 @@ inline int pdl_mask() {
     }
     return v;
 }
+// `cluster_x` > 1 launches thread-block clusters of that many CTAs along x (CTA pairs of the conv kernel).
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int pdl, Args&&... args) {
+inline cudaError_t launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int pdl, int cluster_x,
+                             Args&&... args) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if ((pdl & pdl_mask()) != 0) {                       // pdl: 0 / false = plain launch, else the kernel's PDL_* class
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = (pdl & pdl_mask()) != 0 ? 1 : 0;      // pdl: 0 / false = plain launch, else the kernel's PDL_* class
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int pdl, Args&&... args) {
+    return launch_kc(kernel, grid, block, smem, st, pdl, 1, std::forward<Args>(args)...);
 }
 
 inline int num_sms() {
@@ -156,15 +171,20 @@ inline int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
     return IST_OK;
 }
 
-// which implicit-GEMM kernel runs the convolutions: 1 = conv_halo.cuh (default), 0 = conv_igemm.cuh (IST_B200_CONV=igemm)
-inline int conv_impl_halo() {
+// which implicit-GEMM kernel runs the convolutions (IST_B200_CONV): "pair" (default) = conv_halo.cuh as CTA pairs
+// (tcgen05 cta_group::2), "halo" = conv_halo.cuh single-CTA, "igemm" = conv_igemm.cuh (first generation)
+inline int conv_impl() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("IST_B200_CONV");
-        v = (e != nullptr && strcmp(e, "igemm") == 0) ? 0 : 1;
+        v = (e != nullptr && strcmp(e, "igemm") == 0) ? 0 : (e != nullptr && strcmp(e, "halo") == 0) ? 1 : 2;
     }
     return v;
 }
+inline int conv_impl_halo() { return conv_impl() >= 1; }
+inline int conv_impl_pair() { return conv_impl() == 2; }
+// independent workers of a conv launch: CTAs, or CTA pairs
+inline int conv_workers() { return conv_impl_pair() ? num_sms() / 2 : num_sms(); }
 // timing experiments (results are garbage when loads are skipped): IST_B200_DBG_FLAGS bit 1 (2) skips the A loads, bit 2 (4) the B loads
 inline int halo_dbg_flags() {
     static int v = -1;
@@ -237,21 +257,21 @@ struct GramFuse {
     int chunks;
     const float* alpha;     // [NB] device multipliers (gram_dmat_kernel's alpha_out)
 };
-template <int N_TILE>
+template <int N_TILE, bool PAIR>
 inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                          const CUtensorMap& b_lo, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const CUtensorMap& f_hi,
                          const CUtensorMap& f_lo, const CUtensorMap& d_hi, const CUtensorMap& d_lo, const ConvParams& p) {
     static bool attr_done = false;
     if (!attr_done) {
-        IST_CUDA(cudaFuncSetAttribute(conv_halo_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      HaloCfg<N_TILE>::SMEM_BYTES));
+        IST_CUDA(cudaFuncSetAttribute(conv_halo_kernel<N_TILE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      HaloCfg<N_TILE, PAIR>::SMEM_BYTES));
         attr_done = true;
     }
     const int total = p.NB * p.tiles_x * p.tiles_y * p.tiles_n;
-    int groups = num_sms() / p.sk_cpf;                 // frame groups that fit side by side
+    int groups = conv_workers() / p.sk_cpf;            // frame groups that fit side by side
     if (groups > p.NB) groups = p.NB;
     if (groups < 1) groups = 1;
-    const int grid = groups * p.sk_cpf;
+    const int grid = groups * p.sk_cpf * (PAIR ? 2 : 1);
     const double px = (double)p.NB * p.H * p.W;
     const int planes = p.passes == 3 ? 2 : 1;
     launch_pre(p.taps == 9 ? (p.mode == CONV_FWD ? "conv_halo_fwd" : "conv_halo_dgrad") : "conv_halo_gram_bwd",
@@ -267,7 +287,7 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
         IST_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(long long) * 8 * 1024, st));
         ConvParams q = p;
         q.dbg_times = dbuf;
-        IST_CUDA(launch_k(conv_halo_kernel<N_TILE>, dim3(grid), dim3(224), HaloCfg<N_TILE>::SMEM_BYTES, st, 0, a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, q));
+        IST_CUDA(launch_kc(conv_halo_kernel<N_TILE, PAIR>, dim3(grid), dim3(224), HaloCfg<N_TILE, PAIR>::SMEM_BYTES, st, 0, PAIR ? 2 : 1, a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, q));
         IST_CUDA(cudaStreamSynchronize(st));
         std::vector<long long> h(8 * (size_t)grid);
         IST_CUDA(cudaMemcpy(h.data(), dbuf, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost));
@@ -283,11 +303,13 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
         launch_post(st);
         return IST_OK;
     }
-    IST_CUDA(launch_k(conv_halo_kernel<N_TILE>, dim3(grid), dim3(224), HaloCfg<N_TILE>::SMEM_BYTES, st, p.pdl != 0 ? PDL_TENSOR : 0, a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, p));
+    IST_CUDA(launch_kc(conv_halo_kernel<N_TILE, PAIR>, dim3(grid), dim3(224), HaloCfg<N_TILE, PAIR>::SMEM_BYTES, st, p.pdl != 0 ? PDL_TENSOR : 0, PAIR ? 2 : 1, a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, p));
     launch_post(st);
     return IST_OK;
 }
 inline int conv_n_tile(int cout) { return cout >= 128 ? 128 : 64; }
+// rows of the weight box one CTA loads per tap: a CTA pair splits the N_TILE output channels of a tile between its two CTAs
+inline int conv_b_box(int cout) { return conv_impl_pair() ? conv_n_tile(cout) / 2 : conv_n_tile(cout); }
 // k-steps per tensor-core accumulation chain before promotion to fp32 registers (IST_B200_PROMOTE overrides; 1 = most accurate)
 inline int promote_steps() {
     static int v = 0;
@@ -340,7 +362,7 @@ inline ConvWorkspace& global_conv_workspace() {
 // leaves through shared memory + TMA store.
 // fmt: operand format of the k-steps, 0 = fp16 x fp16, 1 = bf16 x bf16 (mixing the two in one MMA is an illegal instruction on sm_100a)
 inline uint32_t conv_idesc(int fmt, int nt) {
-    return umma_idesc_f16(fmt == 1 ? UMMA_FMT_BF16 : UMMA_FMT_F16, 128, (uint32_t)nt, 0, 0);
+    return umma_idesc_f16(fmt == 1 ? UMMA_FMT_BF16 : UMMA_FMT_F16, conv_impl_pair() ? 256 : 128, (uint32_t)nt, 0, 0);
 }
 inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                        const CUtensorMap& b_lo, ConvParams p, int fmt, const CUtensorMap* o_hi = nullptr,
@@ -348,6 +370,7 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
     if (p.Cin % 64 != 0 || p.Cout % 64 != 0) return fail(IST_ERR_ARG, "conv_igemm needs Cin, Cout %% 64 == 0 (got %d, %d)", p.Cin, p.Cout);
     pick_tile(p.W, &p.TW, &p.TH);
     p.tiles_x = (p.W + p.TW - 1) / p.TW;
+    if (conv_impl_pair()) p.tiles_x = (p.tiles_x + 1) / 2;      // pair tiles: two adjacent tile columns (a phantom one past an odd edge)
     p.tiles_y = (p.H + p.TH - 1) / p.TH;
     const int nt = conv_n_tile(p.Cout);
     p.tiles_n = p.Cout / nt;
@@ -372,13 +395,14 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
         {
             const long long tiles_f = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
             const int ch = p.Cin / 64 + p.extra_chunks;
-            const long long waves = (tiles_f + num_sms() - 1) / num_sms();
-            const double eff = (double)tiles_f / (double)(waves * num_sms());
+            const int workers = conv_workers();
+            const long long waves = (tiles_f + workers - 1) / workers;
+            const double eff = (double)tiles_f / (double)(waves * workers);
             const bool want = wsp->ws != nullptr && ch >= 2 && eff < 0.93 && tiles_f * ch < (1ll << 30);
             p.sk_ws = want ? wsp->ws : nullptr;
             p.sk_flags = want ? wsp->flags : nullptr;
             const long long units = want ? tiles_f * ch : tiles_f;
-            p.sk_cpf = units < num_sms() ? (int)units : num_sms();
+            p.sk_cpf = units < workers ? (int)units : workers;
         }
         p.use_tma_store = (p.out_f32 == nullptr && o_hi != nullptr && o_lo != nullptr) ? 1 : 0;
         const CUtensorMap& oh = p.use_tma_store ? *o_hi : a_hi;
@@ -387,8 +411,11 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
         const CUtensorMap& fl = gf != nullptr ? *gf->f_lo : a_lo;
         const CUtensorMap& dh = gf != nullptr ? *gf->d_hi : b_hi;
         const CUtensorMap& dl = gf != nullptr ? *gf->d_lo : b_lo;
-        return nt == 128 ? launch_halo_t<128>(st, a_hi, a_lo, b_hi, b_lo, oh, ol, fh, fl, dh, dl, p)
-                         : launch_halo_t<64>(st, a_hi, a_lo, b_hi, b_lo, oh, ol, fh, fl, dh, dl, p);
+        if (conv_impl_pair())
+            return nt == 128 ? launch_halo_t<128, true>(st, a_hi, a_lo, b_hi, b_lo, oh, ol, fh, fl, dh, dl, p)
+                             : launch_halo_t<64, true>(st, a_hi, a_lo, b_hi, b_lo, oh, ol, fh, fl, dh, dl, p);
+        return nt == 128 ? launch_halo_t<128, false>(st, a_hi, a_lo, b_hi, b_lo, oh, ol, fh, fl, dh, dl, p)
+                         : launch_halo_t<64, false>(st, a_hi, a_lo, b_hi, b_lo, oh, ol, fh, fl, dh, dl, p);
     }
     return nt == 128 ? launch_conv_t<128>(st, a_hi, a_lo, b_hi, b_lo, p) : launch_conv_t<64>(st, a_hi, a_lo, b_hi, b_lo, p);
 }

@@ -75,8 +75,8 @@ int ist_op_conv3x3_relu_fwd(const float* x, const float* w, const float* b, floa
         IST_TRY(map_act(&a_lo, il, NB, H, W, cin, 9));
         IST_TRY(map_act(&o_hi, oh, NB, H, W, cout, 1));
         IST_TRY(map_act(&o_lo, ol, NB, H, W, cout, 1));
-        IST_TRY(map_b(&b_hi, fh, 9, cout, cin, conv_n_tile(cout)));
-        IST_TRY(map_b(&b_lo, fl, 9, cout, cin, conv_n_tile(cout)));
+        IST_TRY(map_b(&b_hi, fh, 9, cout, cin, conv_b_box(cout)));
+        IST_TRY(map_b(&b_lo, fl, 9, cout, cin, conv_b_box(cout)));
         ConvParams p;
         memset(&p, 0, sizeof(p));
         p.NB = NB; p.H = H; p.W = W; p.Cin = cin; p.Cout = cout; p.taps = 9; p.passes = 3; p.mode = CONV_FWD;
@@ -111,8 +111,8 @@ int ist_op_conv3x3_dgrad(const float* dy, const float* w, float* dx, int NB, int
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     IST_TRY(map_act(&a_hi, gh, NB, H, W, cout, 9));
     IST_TRY(map_act(&a_lo, gl, NB, H, W, cout, 9));
-    IST_TRY(map_b(&b_hi, dh, 9, cin, cout, conv_n_tile(cin)));
-    IST_TRY(map_b(&b_lo, dl, 9, cin, cout, conv_n_tile(cin)));
+    IST_TRY(map_b(&b_hi, dh, 9, cin, cout, conv_b_box(cin)));
+    IST_TRY(map_b(&b_lo, dl, 9, cin, cout, conv_b_box(cin)));
     ConvParams p;
     memset(&p, 0, sizeof(p));
     p.NB = NB; p.H = H; p.W = W; p.Cin = cout; p.Cout = cin; p.taps = 9; p.passes = passes == 1 ? 1 : 3; p.mode = CONV_GRAD;
@@ -249,8 +249,8 @@ static int gram_common(const float* x, const float* target, float weight, float*
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     IST_TRY(map_act(&a_hi, fh, NB, H, W, C, 1));
     IST_TRY(map_act(&a_lo, fl, NB, H, W, C, 1));
-    IST_TRY(map_b(&b_hi, dh, NB, C, C, conv_n_tile(C)));
-    IST_TRY(map_b(&b_lo, dl, NB, C, C, conv_n_tile(C)));
+    IST_TRY(map_b(&b_hi, dh, NB, C, C, conv_b_box(C)));
+    IST_TRY(map_b(&b_lo, dl, NB, C, C, conv_b_box(C)));
     ConvParams p;
     memset(&p, 0, sizeof(p));
     p.NB = NB; p.H = H; p.W = W; p.Cin = C; p.Cout = C; p.taps = 1; p.b_frame = 1; p.passes = 3; p.mode = CONV_GRAD;

@@ -184,8 +184,8 @@ int ensure_gram_buffers(ist_plan* P, Layer& L) {
     IST_TRY(map_gram(&L.mGram_lo, L.out.lo, P->NB, L.H * L.W, L.C));
     IST_TRY(map_act(&L.mFeat_hi, L.out.hi, P->NB, L.H, L.W, L.C, 1));
     IST_TRY(map_act(&L.mFeat_lo, L.out.lo, P->NB, L.H, L.W, L.C, 1));
-    IST_TRY(map_b(&L.mD_hi, L.d_hi, P->NB, L.C, L.C, conv_n_tile(L.C)));
-    IST_TRY(map_b(&L.mD_lo, L.d_lo, P->NB, L.C, L.C, conv_n_tile(L.C)));
+    IST_TRY(map_b(&L.mD_hi, L.d_hi, P->NB, L.C, L.C, conv_b_box(L.C)));
+    IST_TRY(map_b(&L.mD_lo, L.d_lo, P->NB, L.C, L.C, conv_b_box(L.C)));
     return IST_OK;
 }
 
@@ -485,10 +485,10 @@ int ist_plan_create(ist_plan** out, int n_layers, const ist_layer_desc* layers, 
         const Layer& I = P->layers[l - 1];
         if (rc == IST_OK) rc = map_act(&L.mA_hi, I.out.hi, batch, L.H, L.W, L.cin, 9);
         if (rc == IST_OK) rc = map_act(&L.mA_lo, I.out.lo, batch, L.H, L.W, L.cin, 9);
-        if (rc == IST_OK) rc = map_b(&L.mBf_hi, L.wf_hi, 9, L.cout, L.cin, conv_n_tile(L.cout));
-        if (rc == IST_OK) rc = map_b(&L.mBf_lo, L.wf_lo, 9, L.cout, L.cin, conv_n_tile(L.cout));
-        if (rc == IST_OK) rc = map_b(&L.mBd_hi, L.wd_hi, 9, L.cin, L.cout, conv_n_tile(L.cin));
-        if (rc == IST_OK) rc = map_b(&L.mBd_lo, L.wd_lo, 9, L.cin, L.cout, conv_n_tile(L.cin));
+        if (rc == IST_OK) rc = map_b(&L.mBf_hi, L.wf_hi, 9, L.cout, L.cin, conv_b_box(L.cout));
+        if (rc == IST_OK) rc = map_b(&L.mBf_lo, L.wf_lo, 9, L.cout, L.cin, conv_b_box(L.cout));
+        if (rc == IST_OK) rc = map_b(&L.mBd_hi, L.wd_hi, 9, L.cin, L.cout, conv_b_box(L.cin));
+        if (rc == IST_OK) rc = map_b(&L.mBd_lo, L.wd_lo, 9, L.cin, L.cout, conv_b_box(L.cin));
         if (rc == IST_OK) rc = map_act(&L.mO_hi, L.out.hi, batch, L.H, L.W, L.cout, 1);
         if (rc == IST_OK) rc = map_act(&L.mO_lo, L.out.lo, batch, L.H, L.W, L.cout, 1);
         if (rc == IST_OK) rc = map_act(&L.mGo_hi, L.dY.hi, batch, L.H, L.W, L.cout, 1);
