@@ -290,9 +290,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     if constexpr (PAIR) {
                         // the leader announces the bytes of both CTAs; each CTA's loads complete on the leader's barrier
                         const uint32_t lbar = mapa_u32(afull(as), 0);
+                        if (p.dbg_flags & 2) { if (rank == 0) mbar_arrive(afull(as)); } else {
                         if (rank == 0) mbar_arrive_expect_tx(afull(as), a_tx);
                         tma_load_4d_pair(sA, ex ? &tmF_hi : &tmA_hi, lbar, c64, x0, y0, fr);
                         if (split) tma_load_4d_pair(sA + Cfg::A_PLANE, ex ? &tmF_lo : &tmA_lo, lbar, c64, x0, y0, fr);
+                        }
                     } else if (p.dbg_flags & 2) { mbar_arrive(afull(as)); } else {
                     mbar_arrive_expect_tx(afull(as), a_tx);
                     tma_load_4d(sA, ex ? &tmF_hi : &tmA_hi, afull(as), c64, x0, y0, fr);
@@ -306,9 +308,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         const uint32_t sB = b_base + bs * Cfg::B_STAGE;
                         if constexpr (PAIR) {
                             const uint32_t lbar = mapa_u32(bfull(bs), 0);
+                            if (p.dbg_flags & 4) { if (rank == 0) mbar_arrive(bfull(bs)); } else {
                             if (rank == 0) mbar_arrive_expect_tx(bfull(bs), b_tx);
                             tma_load_3d_pair(sB, ex ? &tmD_hi : &tmB_hi, lbar, c64, n0, bz);
                             if (split) tma_load_3d_pair(sB + Cfg::B_PLANE, ex ? &tmD_lo : &tmB_lo, lbar, c64, n0, bz);
+                            }
                         } else if (p.dbg_flags & 4) { mbar_arrive(bfull(bs)); } else {
                         mbar_arrive_expect_tx(bfull(bs), b_tx);
                         tma_load_3d(sB, ex ? &tmD_hi : &tmB_hi, bfull(bs), c64, n0, bz);
@@ -346,8 +350,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 for (int ky = 0; ky < kyn; ++ky) {
                     for (int kx = 0; kx < kyn; ++kx, ++kit) {
                         const bool last_tap = (ky == kyn - 1 && kx == kyn - 1);
-                        const int in_chain = kit % promote;
-                        const bool chain_end = (in_chain == promote - 1) || (kit == kit_seg - 1);
+                        // chains never cross a 64-channel chunk: every tile of a layer sees the same chain partition wherever
+                        // the stream-K ranges are cut (translation-invariant rounding)
+                        const int in_chain = (ky * kyn + kx) % promote;
+                        const bool chain_end = (in_chain == promote - 1) || last_tap;
                         if (in_chain == 0) mbar_wait(mempty(mb), mph ^ 1u);
                         mbar_wait(bfull(bs), bph);
                         tc_fence_after();
@@ -469,7 +475,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         IST_FOR_SEGMENTS(fr, fcount, tile, cbeg, cend) {
             const int mend = cend < cchunks ? cend : cchunks;
             const int kit_seg = (mend > cbeg ? mend - cbeg : 0) * taps;
-            const int nchains = (kit_seg + promote - 1) / promote;
+            const int nchains = (mend > cbeg ? mend - cbeg : 0) * ((taps + promote - 1) / promote);      // per chunk: ceil(taps / promote)
             const bool has_main = kit_seg > 0, has_extra = cend > cchunks;
             float acc[N_TILE];
 #pragma unroll

@@ -319,6 +319,21 @@ inline int promote_steps() {
     }
     return v;
 }
+// Forward convolutions: taps per accumulation chain inside a 64-channel chunk (chains never cross a chunk). Draining a
+// 128x128 fp32 accumulator takes ~1000 cycles of tensor-memory read bandwidth, the 12 MMAs of a k-step 768 cycles as a CTA
+// pair (1032 single-CTA): one chain per tap is drain-bound in pair mode. Measured (profiles/r01_promote_fwd_ab.log): chains
+// of 1 / 2 / 3 / 5 taps give a forward rel-L2 error of 1.5 / 2.0 / 2.7 / 3.7e-7 against fp64 and a 512^2 closure of
+// 1.70 / 1.52 / 1.47 / 1.45 ms; 3 taps (three chains per chunk) is the default for CTA pairs, 1 for the single-CTA kernel.
+// IST_B200_PROMOTE_FWD overrides.
+inline int promote_steps_fwd() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("IST_B200_PROMOTE_FWD");
+        const char* g = getenv("IST_B200_PROMOTE");
+        v = (e != nullptr && atoi(e) > 0) ? atoi(e) : (g != nullptr && atoi(g) > 0) ? atoi(g) : (conv_impl_pair() ? 3 : 1);
+    }
+    return v;
+}
 // The data-gradient is linear in its operands (no ReLU / pool decisions depend on it), so the ~3e-8-per-MMA truncation of a
 // longer tensor-core chain only adds ~1e-6 relative error to the gradient: one chain per 64-channel chunk (9 taps = 36 MMAs)
 // instead of one per k-step saves most of the promotion drains. IST_B200_PROMOTE_BWD overrides.
@@ -374,7 +389,7 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
     p.tiles_y = (p.H + p.TH - 1) / p.TH;
     const int nt = conv_n_tile(p.Cout);
     p.tiles_n = p.Cout / nt;
-    if (p.promote < 1) p.promote = (p.mode == CONV_GRAD) ? promote_steps_bwd() : promote_steps();
+    if (p.promote < 1) p.promote = (p.mode == CONV_GRAD) ? promote_steps_bwd() : promote_steps_fwd();
     p.idesc = conv_idesc(fmt, nt);
     p.idesc2 = conv_idesc(0, nt);
     p.extra_chunks = 0;

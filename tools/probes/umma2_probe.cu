@@ -8,11 +8,6 @@
 #include "../../can-image-style-transfer-save-automotive-radar_b200/csrc/ptx.cuh"
 using namespace ist;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(kCols) : "memory");
@@ -31,7 +26,10 @@ __device__ __forceinline__ void umma2_commit(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 
-struct Args { int n, reps, cper, issuers; long long* out; };
+__device__ __forceinline__ void umma2_commit_local(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+struct Args { int n, reps, cper, issuers, mc; long long* out; };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe2(Args a) {
     extern __shared__ uint8_t smem_raw[];
@@ -56,7 +54,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe2(Args 
             for (int r = 0; r < a.reps; ++r) {
                 const uint32_t k4 = r & 3;
                 umma2_f16_lh(d, (sA >> 4) + 2 * k4 + (uint32_t)((r >> 2) & 7) * 8, hi_w, (sB >> 4) + 2 * k4, hi_w, idesc, 1u);
-                if (a.cper > 0 && (r % a.cper) == a.cper - 1 && r != a.reps - 1) umma2_commit(bar + 64 + 8 * warp, 3);   // dummy barriers, never waited
+                // cper is a power of two (mask test: no integer division in the issuing thread); mc = 1: multicast to both CTAs,
+                // mc = 0: plain cta_group::2 commit to the leader's barrier
+                if (a.cper > 0 && (r & (a.cper - 1)) == a.cper - 1 && r != a.reps - 1) {
+                    if (a.mc) umma2_commit(bar + 64 + 8 * warp, 3); else umma2_commit_local(bar + 64 + 8 * warp);
+                }
             }
             umma2_commit(bar + 8 * warp, 1);
             const long long t1 = clock64();
@@ -76,13 +78,14 @@ int main() {
     const int smem = 32768 + 65536 + 1024 + 512;
     cudaFuncSetAttribute(probe2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     printf("cta_group::2, M = 256 (128 rows per CTA); cycles per MMA (per-CTA work 128 x N x 16; floor N/2)\n");
-    printf("%4s %5s %8s | %13s %13s\n", "N", "cper", "issuers", "issue clk/MMA", "total clk/MMA");
+    printf("%4s %5s %2s %8s | %13s %13s\n", "N", "cper", "mc", "issuers", "issue clk/MMA", "total clk/MMA");
     const int reps = 4096;
     for (int n : {64, 128, 256})
-        for (int cper : {0, 4, 12})
-            for (int issuers = 1; issuers <= 4; ++issuers) {
-                if (n == 256 && issuers > 2) continue;
-                Args a{n, reps, cper, issuers, out};
+        for (int cper : {0, 1, 4, 8})
+          for (int mc = 0; mc < 2; ++mc)
+            for (int issuers = 1; issuers <= 2; ++issuers) {
+                if (cper == 0 && mc == 1) continue;
+                Args a{n, reps, cper, issuers, mc, out};
                 cudaMemset(out, 0, sizeof(long long) * 74 * 8);
                 probe2<<<148, 128, smem>>>(a);
                 cudaError_t e = cudaDeviceSynchronize();
@@ -94,7 +97,7 @@ int main() {
                     for (int w = 0; w < issuers; ++w) { if (h[c * 8 + 2 * w] > mi) mi = h[c * 8 + 2 * w]; if (h[c * 8 + 2 * w + 1] > mt) mt = h[c * 8 + 2 * w + 1]; }
                     is += mi; tot += mt;
                 }
-                printf("%4d %5d %8d | %13.1f %13.1f\n", n, cper, issuers, is / 74 / reps / issuers, tot / 74 / reps / issuers);
+                printf("%4d %5d %2d %8d | %13.1f %13.1f\n", n, cper, mc, issuers, is / 74 / reps / issuers, tot / 74 / reps / issuers);
             }
     return 0;
 }
