@@ -35,7 +35,7 @@ struct HaloCfg {
     static constexpr int B_ROWS = PAIR ? N_TILE / 2 : N_TILE;      // weight rows this CTA holds per tap
     static constexpr int B_PLANE = B_ROWS * 128;
     static constexpr int B_STAGE = 2 * B_PLANE;
-    static constexpr int B_STAGES = PAIR ? ((N_TILE == 128) ? 6 : 8) : ((N_TILE == 128) ? 3 : 4);
+    static constexpr int B_STAGES = PAIR ? ((N_TILE == 128) ? 4 : 8) : ((N_TILE == 128) ? 3 : 4);
     // tensor-memory accumulators (N_TILE fp32 columns each, 512 columns in all):
     //   N_TILE = 128: [main 0][main 1][main 2 | Gram][cross]      (third main buffer when no Gram k-steps are fused)
     //   N_TILE =  64: [main 0..3][cross 0][cross 1][Gram 0][Gram 1]   (the Gram accumulator follows the cross buffer's parity)
@@ -47,7 +47,17 @@ struct HaloCfg {
     static constexpr bool XSINGLE = (N_TILE == 128);
     static constexpr int OUT_PLANE = 128 * 128;                    // output staging: 128 pixels x 64 channels x 2 B per plane
     static constexpr int OUT_BYTES = 2 * OUT_PLANE;                // hi + lo
-    static constexpr int SMEM_BYTES = A_STAGES * A_STAGE + B_STAGES * B_STAGE + OUT_BYTES + 512 + 1024;
+    // a pair's CTA holds half the weight rows, which leaves room for a second staging buffer: the two 64-channel halves of a
+    // 128-channel tile are then converted back to back instead of waiting for the first TMA store to drain the buffer
+    static constexpr int OUT_BUFS = (PAIR && N_TILE == 128) ? 2 : 1;
+    // Epilogue warps: one group of four (one warp per tensor-memory lane quadrant) holds all N_TILE accumulator columns of
+    // its pixel; a pair's CTAs run TWO groups (warps 2-5 and 7-10), each holding half of the columns. With one warp per
+    // scheduler the conversion code is issue-latency bound (~8k cycles per 128-channel tile); two warps per scheduler overlap,
+    // halve the per-thread work and drop the register pressure from 255 (spills) to < 184.
+    static constexpr int EPI_GROUPS = PAIR ? 2 : 1;
+    static constexpr int NH = N_TILE / EPI_GROUPS;                 // accumulator columns per epilogue thread
+    static constexpr int THREADS = 96 + 128 * EPI_GROUPS;          // producer, two issuers (warps 1 and 6), epilogue groups
+    static constexpr int SMEM_BYTES = A_STAGES * A_STAGE + B_STAGES * B_STAGE + OUT_BUFS * OUT_BYTES + 512 + 1024;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_bo(uint32_t smem_addr, uint32_t sbo, uint32_t use_base_offset) {
@@ -126,7 +136,7 @@ __device__ __forceinline__ void conv_grad_regs_32(const ConvParams& p, float (&v
 }
 
 template <int N_TILE, bool PAIR>
-__global__ void __launch_bounds__(224, 1)
+__global__ void __launch_bounds__((HaloCfg<N_TILE, PAIR>::THREADS), 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                  const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
@@ -139,7 +149,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t a_base = smem_base;
     const uint32_t b_base = smem_base + Cfg::A_STAGES * Cfg::A_STAGE;
     const uint32_t o_base = b_base + Cfg::B_STAGES * Cfg::B_STAGE;      // output staging (1024-aligned planes)
-    const uint32_t bar_base = o_base + Cfg::OUT_BYTES;
+    const uint32_t bar_base = o_base + Cfg::OUT_BUFS * Cfg::OUT_BYTES;
     // barriers (8 B each): a_full[3] @0, a_empty[3] @24, b_full[8] @48, b_empty[8] @112, main_full[4] @176,
     // main_empty[4] @208, cross_full[2] @240, cross_empty[2] @256, tmem base address @272
     auto afull = [&](int s) { return bar_base + 8u * s; };
@@ -192,11 +202,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int s = 0; s < Cfg::B_STAGES; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), releasers); }
         for (uint32_t a = 0; a < 4; ++a) {
             mbar_init(mfull(a), 1);
-            mbar_init(mempty(a), PAIR ? 8 : 4);           // one arrival per epilogue warp (of both CTAs of a pair)
+            mbar_init(mempty(a), 4 * Cfg::EPI_GROUPS * (PAIR ? 2 : 1));   // one arrival per epilogue warp (of both CTAs of a pair)
         }
         for (uint32_t a = 0; a < 2; ++a) {
             mbar_init(xfull(a), 1);
-            mbar_init(xempty(a), PAIR ? 8 : 4);
+            mbar_init(xempty(a), 4 * Cfg::EPI_GROUPS * (PAIR ? 2 : 1));
         }
         fence_barrier_init();
     }
@@ -468,23 +478,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
     } else {
         // ------------------------------------------- promotion + epilogue ---------------------------------------------
-        const int quad = warp & 3;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        constexpr int EG = Cfg::EPI_GROUPS, NH = Cfg::NH;
+        const int quad = warp & 3;                       // tensor-memory lane quadrant this warp may read
+        const int grp = (EG == 2 && warp >= 7) ? 1 : 0;  // column half of this warp's group
+        const int col0 = grp * NH;                       // first accumulator column of this thread
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0;
         const int m = quad * 32 + lane;                  // accumulator row == pixel inside the tile
+        // named barriers: all epilogue threads (partial-tile hand-over), and the threads that fill one staging buffer
+        auto bar_all = [&]() { if constexpr (EG == 1) named_bar_sync(1, 128); else named_bar_sync(3, 256); };
+        auto bar_half = [&]() {
+            if constexpr (EG == 1) named_bar_sync(1, 128);
+            else if constexpr (N_TILE == 128) named_bar_sync(1 + grp, 128);
+            else named_bar_sync(3, 256);
+        };
+        // the thread that issues the TMA store of a staging buffer (one per group when each group owns a 64-channel half)
+        const bool storer = (EG == 2 && N_TILE == 128) ? (lane == 0 && (warp == 2 || warp == 7)) : (threadIdx.x == 64);
         uint32_t mb = 0, mph = 0, scount = 0;
         IST_FOR_SEGMENTS(fr, fcount, tile, cbeg, cend) {
             const int mend = cend < cchunks ? cend : cchunks;
             const int kit_seg = (mend > cbeg ? mend - cbeg : 0) * taps;
             const int nchains = (mend > cbeg ? mend - cbeg : 0) * ((taps + promote - 1) / promote);      // per chunk: ceil(taps / promote)
             const bool has_main = kit_seg > 0, has_extra = cend > cchunks;
-            float acc[N_TILE];
+            float acc[NH];
 #pragma unroll
-            for (int j = 0; j < N_TILE; ++j) acc[j] = 0.f;
+            for (int j = 0; j < NH; ++j) acc[j] = 0.f;
             for (int ch = 0; ch < nchains; ++ch) {
                 mbar_wait(mfull(mb), mph);
                 tc_fence_after();
 #pragma unroll
-                for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                for (int c0 = 0; c0 < NH; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32(lane_base + mb * N_TILE + c0, r);
                     tmem_ld_wait();
@@ -507,7 +529,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 tc_fence_after();
                 if (has_main) {
 #pragma unroll
-                    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                    for (int c0 = 0; c0 < NH; c0 += 32) {
                         uint32_t r[32];
                         tmem_ld_32x32(lane_base + (uint32_t)Cfg::CROSS_COL + xa * N_TILE + c0, r);
                         tmem_ld_wait();
@@ -519,7 +541,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     // fused Gram term: acc (true units, alpha == 1 for data-gradients) += alpha2[frame] * (D * F)
                     const float a2 = __ldg(p.alpha2_dev + fr);
 #pragma unroll
-                    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                    for (int c0 = 0; c0 < NH; c0 += 32) {
                         uint32_t r[32];
                         tmem_ld_32x32(lane_base + (uint32_t)Cfg::GRAM_COL + xa * N_TILE + c0, r);
                         tmem_ld_wait();
@@ -545,12 +567,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         if (++spins > (1u << 26)) __trap();
                     } while (v != 0);
                 }
-                named_bar_sync(1, 128);
-                float* ws = p.sk_ws + (size_t)(2 * blockIdx.x + slot) * (128 * N_TILE);
+                bar_all();
+                float* ws = p.sk_ws + (size_t)(2 * blockIdx.x + slot) * (128 * N_TILE) + (size_t)col0 * 128;
 #pragma unroll
-                for (int j = 0; j < N_TILE; ++j) ws[j * 128 + m] = acc[j];
+                for (int j = 0; j < NH; ++j) ws[j * 128 + m] = acc[j];
                 __threadfence();
-                named_bar_sync(1, 128);
+                bar_all();
                 if (threadIdx.x == 64) {
                     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
                 }
@@ -574,11 +596,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                             if (++spins > (1u << 26)) __trap();
                         } while (v == 0);
                     }
-                    named_bar_sync(1, 128);
-                    const float* ws = p.sk_ws + (size_t)(2 * oc + slot) * (128 * N_TILE);
+                    bar_all();
+                    const float* ws = p.sk_ws + (size_t)(2 * oc + slot) * (128 * N_TILE) + (size_t)col0 * 128;
 #pragma unroll
-                    for (int j = 0; j < N_TILE; ++j) acc[j] += __ldcg(ws + j * 128 + m);
-                    named_bar_sync(1, 128);
+                    for (int j = 0; j < NH; ++j) acc[j] += __ldcg(ws + j * 128 + m);
+                    bar_all();
                     if (threadIdx.x == 64) {
                         asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(0) : "memory");
                     }
@@ -595,49 +617,56 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 // directly to NHWC memory touches 32 different lines per warp instruction. Each thread writes its pixel's
                 // 64 channels (one 128-byte row, 16-byte chunks XOR-swizzled by the row index exactly as the tensor map's
                 // SWIZZLE_128B expects) and one elected thread stores the 16x8-pixel box; the image border is clipped by TMA.
+                // Staging buffers hold 64 channels (one 128-byte row per pixel). This thread's NH columns start at tile channel
+                // col0: one group fills both halves of a 128-channel tile in turn; with two groups each group fills its own half
+                // (N_TILE = 128, own buffer, own TMA store) or its own 32 channels of the single half (N_TILE = 64).
 #pragma unroll
-                for (int h0 = 0; h0 < N_TILE; h0 += 64) {
-                    if (threadIdx.x == 64) tma_store_wait_read();          // previous box has left the staging buffer
-                    named_bar_sync(1, 128);
+                for (int hh = 0; hh < (NH + 63) / 64; ++hh) {
+                    const int h0 = (col0 & ~63) + 64 * hh;                  // 64-channel half this round belongs to
+                    const uint32_t o_buf = o_base + (Cfg::OUT_BUFS == 2 ? (uint32_t)(h0 >> 6) * Cfg::OUT_BYTES : 0u);
+                    if (storer) tma_store_wait_read();                     // the box last staged in this buffer has left it
+                    bar_half();
 #pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                    for (int cb = 0; cb < (NH < 64 ? NH : 64); cb += 32) {
+                        const int c0 = (col0 & 63) + cb;                    // channel offset inside the 64-channel half
+                        const int ja = 64 * hh + cb;                        // accumulator index of the block's first column
                         float v[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = acc[h0 + c0 + j] * alpha;
+                        for (int j = 0; j < 32; ++j) v[j] = acc[ja + j] * alpha;
                         uint32_t hi[16], lo[16];
                         if (p.mode == CONV_FWD) conv_epilogue_regs_32(p, v, n0 + h0 + c0, hi, lo);
                         else conv_grad_regs_32(p, v, gpix * (size_t)p.Cout + n0 + h0 + c0, gvalid, hi, lo);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const uint32_t chunk = (uint32_t)(((c0 >> 3) + q) ^ (m & 7));
-                            const uint32_t a = o_base + (uint32_t)m * 128u + chunk * 16u;
+                            const uint32_t a = o_buf + (uint32_t)m * 128u + chunk * 16u;
                             st_shared_v4(a, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
                             st_shared_v4(a + Cfg::OUT_PLANE, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
                         }
                     }
                     fence_proxy_async_smem();
-                    named_bar_sync(1, 128);
-                    if (threadIdx.x == 64) {
-                        tma_store_4d(&tmO_hi, o_base, n0 + h0, tx * Cfg::TW, ty * Cfg::TH, fr);
-                        tma_store_4d(&tmO_lo, o_base + Cfg::OUT_PLANE, n0 + h0, tx * Cfg::TW, ty * Cfg::TH, fr);
+                    bar_half();
+                    if (storer) {
+                        tma_store_4d(&tmO_hi, o_buf, n0 + h0, tx * Cfg::TW, ty * Cfg::TH, fr);
+                        tma_store_4d(&tmO_lo, o_buf + Cfg::OUT_PLANE, n0 + h0, tx * Cfg::TW, ty * Cfg::TH, fr);
                         tma_store_commit();
                     }
                 }
             } else {
                 if (gvalid) {
-                    const size_t obase = gpix * (size_t)p.Cout + n0;
+                    const size_t obase = gpix * (size_t)p.Cout + n0 + col0;
 #pragma unroll
-                    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                    for (int c0 = 0; c0 < NH; c0 += 32) {
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = acc[c0 + j] * alpha;
-                        conv_epilogue_32(p, v, obase + c0, n0 + c0);
+                        conv_epilogue_32(p, v, obase + c0, n0 + col0 + c0);
                     }
                 }
             }
             if (dbg != nullptr && threadIdx.x == 64) dbg[5] = clock64();
         }
-        if (p.use_tma_store && threadIdx.x == 64) tma_store_wait_all();
+        if (p.use_tma_store && storer) tma_store_wait_all();
     }
 #undef IST_FOR_SEGMENTS
 

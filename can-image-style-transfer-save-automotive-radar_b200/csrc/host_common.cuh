@@ -287,7 +287,7 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
         IST_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(long long) * 8 * 1024, st));
         ConvParams q = p;
         q.dbg_times = dbuf;
-        IST_CUDA(launch_kc(conv_halo_kernel<N_TILE, PAIR>, dim3(grid), dim3(224), HaloCfg<N_TILE, PAIR>::SMEM_BYTES, st, 0, PAIR ? 2 : 1, a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, q));
+        IST_CUDA(launch_kc(conv_halo_kernel<N_TILE, PAIR>, dim3(grid), dim3(HaloCfg<N_TILE, PAIR>::THREADS), HaloCfg<N_TILE, PAIR>::SMEM_BYTES, st, 0, PAIR ? 2 : 1, a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, q));
         IST_CUDA(cudaStreamSynchronize(st));
         std::vector<long long> h(8 * (size_t)grid);
         IST_CUDA(cudaMemcpy(h.data(), dbuf, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost));
@@ -303,7 +303,7 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
         launch_post(st);
         return IST_OK;
     }
-    IST_CUDA(launch_kc(conv_halo_kernel<N_TILE, PAIR>, dim3(grid), dim3(224), HaloCfg<N_TILE, PAIR>::SMEM_BYTES, st, p.pdl != 0 ? PDL_TENSOR : 0, PAIR ? 2 : 1, a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, p));
+    IST_CUDA(launch_kc(conv_halo_kernel<N_TILE, PAIR>, dim3(grid), dim3(HaloCfg<N_TILE, PAIR>::THREADS), HaloCfg<N_TILE, PAIR>::SMEM_BYTES, st, p.pdl != 0 ? PDL_TENSOR : 0, PAIR ? 2 : 1, a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, p));
     launch_post(st);
     return IST_OK;
 }
