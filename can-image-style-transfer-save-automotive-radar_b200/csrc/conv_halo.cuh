@@ -666,7 +666,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
             if (dbg != nullptr && threadIdx.x == 64) dbg[5] = clock64();
         }
-        if (p.use_tma_store && storer) tma_store_wait_all();
+        // the staging buffers must have been read before the CTA may exit; the global writes themselves complete with the grid
+        if (p.use_tma_store && storer) tma_store_wait_read();
     }
 #undef IST_FOR_SEGMENTS
 

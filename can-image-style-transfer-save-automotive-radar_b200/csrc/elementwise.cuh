@@ -352,9 +352,12 @@ conv_first_dgrad_kernel(const uint16_t* __restrict__ g_hi, const uint16_t* __res
 // MaxPool2d(2,2) forward (vgg.py:21-22,54): floor(H/2) x floor(W/2); first maximum in row-major window order
 // wins (strict >), matching ATen. One thread = one output pixel x 8 channels.
 // ------------------------------------------------------------------------------------------------------------
+// `idx` (optional, one byte per pooled element): position 0..3 of the first maximum in row-major window order, or 4 when the
+// maximum is not positive (the ReLU mask then stops the gradient). grad_route_kernel routes from it instead of re-reading
+// the four pre-pool activations.
 __global__ void maxpool_fwd_kernel(const uint16_t* __restrict__ in_hi, const uint16_t* __restrict__ in_lo,
                                    uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, int NB, int H, int W,
-                                   int C) {
+                                   int C, uint8_t* __restrict__ idx) {
     const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
     const size_t total = (size_t)NB * Ho * Wo * C8;
     pdl_trigger();
@@ -368,6 +371,7 @@ __global__ void maxpool_fwd_kernel(const uint16_t* __restrict__ in_hi, const uin
         const int n = (int)(r / Ho);
         uint32_t bh[4], bl[4];
         float bv[8];
+        uint32_t bk[2] = {0u, 0u};          // argmax position per channel, one byte each (channels 0-3, 4-7)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const size_t o = ((((size_t)n * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)) * C) / 8 + c8;
@@ -385,17 +389,27 @@ __global__ void maxpool_fwd_kernel(const uint16_t* __restrict__ in_hi, const uin
                         bv[2 * e] = a;
                         bh[e] = (bh[e] & 0xFFFF0000u) | (uh[e] & 0xFFFFu);
                         bl[e] = (bl[e] & 0xFFFF0000u) | (ul[e] & 0xFFFFu);
+                        const int sh = 8 * ((2 * e) & 3);
+                        bk[e >> 1] = (bk[e >> 1] & ~(0xFFu << sh)) | ((uint32_t)k << sh);
                     }
                     if (b > bv[2 * e + 1]) {
                         bv[2 * e + 1] = b;
                         bh[e] = (bh[e] & 0xFFFFu) | (uh[e] & 0xFFFF0000u);
                         bl[e] = (bl[e] & 0xFFFFu) | (ul[e] & 0xFFFF0000u);
+                        const int sh = 8 * ((2 * e + 1) & 3);
+                        bk[e >> 1] = (bk[e >> 1] & ~(0xFFu << sh)) | ((uint32_t)k << sh);
                     }
                 }
             }
         }
         reinterpret_cast<uint4*>(out_hi)[i] = make_uint4(bh[0], bh[1], bh[2], bh[3]);
         reinterpret_cast<uint4*>(out_lo)[i] = make_uint4(bl[0], bl[1], bl[2], bl[3]);
+        if (idx != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (!(bv[c] > 0.f)) bk[c >> 2] = (bk[c >> 2] & ~(0xFFu << (8 * (c & 3)))) | (4u << (8 * (c & 3)));
+            reinterpret_cast<uint2*>(idx)[i] = make_uint2(bk[0], bk[1]);
+        }
     }
 }
 
@@ -410,6 +424,8 @@ __global__ void maxpool_fwd_kernel(const uint16_t* __restrict__ in_hi, const uin
 struct RouteParams {
     int NB, H, W, C;
     const float* g_pool;        // fp32 NHWC [NB, H/2, W/2, C] or nullptr
+    const uint8_t* idx;         // maxpool_fwd_kernel's argmax bytes [NB, H/2, W/2, C] or nullptr; when given (only with
+                                // g_pool, mask, plane output and no addend / content term) the activations are not read
     const uint16_t* f_hi;       // fp16 planes of F (argmax + mask + content term)
     const uint16_t* f_lo;
     const float* addend;        // fp32 NHWC [NB,H,W,C] or nullptr
@@ -446,6 +462,26 @@ __global__ void __launch_bounds__(256, 4) grad_route_kernel(const RouteParams p)
         float fv[4][4];
         bool inb[4];
         size_t o4[4];
+        if (p.idx != nullptr) {
+            // routing from the forward pass's argmax bytes: position k of the window receives g where idx == k (4 = masked)
+            uint32_t code = 0x04040404u;
+            if (window) code = __ldg(reinterpret_cast<const uint32_t*>(p.idx + ((((size_t)n * Ho + yo) * Wo + xo) * p.C)) + c4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
+                if (!((yy < p.H) && (xx < p.W))) continue;
+                const size_t o = ((((size_t)n * p.H + yy) * p.W + xx) * p.C) / 4 + c4;
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = (((code >> (8 * e)) & 0xFFu) == (uint32_t)k) ? g[e] : 0.f;
+                uint32_t h0, l0, h1, l1;
+                split_pack<true>(v[0], v[1], h0, l0);
+                split_pack<true>(v[2], v[3], h1, l1);
+                reinterpret_cast<uint2*>(p.out_hi)[o] = make_uint2(h0, h1);
+                reinterpret_cast<uint2*>(p.out_lo)[o] = make_uint2(l0, l1);
+            }
+            continue;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);

@@ -133,7 +133,7 @@ int ist_op_maxpool2x2_fwd(const float* x, float* y, int NB, int C, int H, int W,
     IST_TRY(t.alloc(&ih, (size_t)NB * H * W * C)); IST_TRY(t.alloc(&il, (size_t)NB * H * W * C));
     IST_TRY(t.alloc(&oh, (size_t)NB * Ho * Wo * C)); IST_TRY(t.alloc(&ol, (size_t)NB * Ho * Wo * C));
     IST_TRY(to_planes(st, x, ih, il, NB, C, H * W, kS, false));
-    maxpool_fwd_kernel<<<ew_grid((size_t)NB * Ho * Wo * (C / 8), 256), 256, 0, st>>>(ih, il, oh, ol, NB, H, W, C);
+    maxpool_fwd_kernel<<<ew_grid((size_t)NB * Ho * Wo * (C / 8), 256), 256, 0, st>>>(ih, il, oh, ol, NB, H, W, C, nullptr);
     IST_CUDA(cudaGetLastError());
     IST_TRY(from_planes(st, oh, ol, y, NB, C, Ho * Wo, 1.f / kS, false));
     return IST_OK;

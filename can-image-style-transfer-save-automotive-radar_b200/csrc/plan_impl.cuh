@@ -51,6 +51,7 @@ struct Layer {
     Planes T;
     bool content_set = false;
     float* c_partial = nullptr;
+    uint8_t* pool_idx = nullptr;   // pool layers: argmax byte per output element (maxpool_fwd_kernel -> grad_route_kernel)
     float* ext_seed = nullptr;     // fp32 NHWC external gradient seed (generic backward)
     bool ext_active = false;
 };
@@ -134,8 +135,8 @@ int run_forward(ist_plan* P, const float* x, int upto, cudaStream_t st, int from
         } else {
             const Layer& I = P->layers[l - 1];
             const size_t items = (size_t)P->NB * L.H * L.W * (L.C / 8);
-            IST_EWK("maxpool_fwd", 5.0 * L.out_elems * 4, st, PDL_EW, maxpool_fwd_kernel, ew_grid(items, 256), 256, 0,
-                    (const uint16_t*)I.out.hi, (const uint16_t*)I.out.lo, L.out.hi, L.out.lo, P->NB, I.H, I.W, I.C);
+            IST_EWK("maxpool_fwd", 5.0 * L.out_elems * 4 + L.out_elems, st, PDL_EW, maxpool_fwd_kernel, ew_grid(items, 256), 256, 0,
+                    (const uint16_t*)I.out.hi, (const uint16_t*)I.out.lo, L.out.hi, L.out.lo, P->NB, I.H, I.W, I.C, L.pool_idx);
         }
     }
     P->forwarded_upto = upto;
@@ -228,11 +229,14 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         p.pdl = 1;
         return launch_conv(st, L.mFeat_hi, L.mFeat_lo, L.mD_hi, L.mD_lo, p, 0, &L.mGo_hi, &L.mGo_lo, nullptr, &P->skw);
     };
-    auto route = [&](Layer& L, const float* g_pool, const float* addend, bool content, bool to_f32, float* f32_out) -> int {
+    auto route = [&](Layer& L, const float* g_pool, const float* addend, bool content, bool to_f32, float* f32_out,
+                     const uint8_t* pool_idx = nullptr) -> int {
         RouteParams r;
         memset(&r, 0, sizeof(r));
         r.NB = NB; r.H = L.H; r.W = L.W; r.C = L.C;
         r.g_pool = g_pool;
+        // the pool's forward pass left the argmax bytes: no need to read the four pre-pool activations again
+        if (g_pool != nullptr && addend == nullptr && !content && !to_f32) r.idx = pool_idx;
         r.f_hi = L.out.hi; r.f_lo = L.out.lo;
         r.addend = addend;
         if (content) {
@@ -243,7 +247,7 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         r.out_hi = L.dY.hi; r.out_lo = L.dY.lo;
         r.out_f32 = to_f32 ? f32_out : nullptr;
         const size_t items = (size_t)NB * ((L.H + 1) / 2) * ((L.W + 1) / 2) * (L.C / 4);
-        IST_EWK("grad_route", (double)L.out_elems * (4 + 4 + (g_pool != nullptr ? 1 : 0) + (addend != nullptr ? 4 : 0) + (content ? 8 : 0)), st, PDL_EW,
+        IST_EWK("grad_route", (double)L.out_elems * (4 + (r.idx != nullptr ? 0.25 : 4) + (g_pool != nullptr ? 1 : 0) + (addend != nullptr ? 4 : 0) + (content ? 8 : 0)), st, PDL_EW,
                 grad_route_kernel, ew_grid(items, 256), 256, 0, r);
         return IST_OK;
     };
@@ -297,7 +301,7 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
                 IST_TRY(route(L, g_pool, ext(L), content, true, P->fbuf[1]));
                 IST_TRY(gram_bwd(L, P->fbuf[1], false));
             } else {
-                IST_TRY(route(L, g_pool, ext(L), content, false, nullptr));
+                IST_TRY(route(L, g_pool, ext(L), content, false, nullptr, Pl.pool_idx));
             }
         } else {
             if (style) {
@@ -459,7 +463,10 @@ int ist_plan_create(ist_plan** out, int n_layers, const ist_layer_desc* layers, 
     }
     P->n_conv = nconv;
     // buffers
-    for (int l = 0; l < n_layers && rc == IST_OK; ++l) rc = alloc_planes(P->mem, &P->layers[l].out, P->layers[l].out_elems);
+    for (int l = 0; l < n_layers && rc == IST_OK; ++l) {
+        rc = alloc_planes(P->mem, &P->layers[l].out, P->layers[l].out_elems);
+        if (rc == IST_OK && P->layers[l].kind == IST_LAYER_MAXPOOL2X2) rc = P->mem.alloc(&P->layers[l].pool_idx, P->layers[l].out_elems);
+    }
     for (int i = 0; i < 2 && rc == IST_OK; ++i) {
         rc = alloc_planes(P->mem, &P->gbuf[i], P->max_elems);
         if (rc == IST_OK) rc = P->mem.alloc(&P->fbuf[i], P->max_elems);
