@@ -178,8 +178,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// Default semantics (release at CTA scope): the arrivals sent this way order tensor-memory reads (tcgen05.fence) before the
+// leader's next MMAs, they publish no global or shared memory. An explicit .release.cluster makes the compiler emit
+// MEMBAR.ALL.GPU + ERRBAR in front of every arrive (a third of all stall samples of the first pair build).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA loads of a CTA pair: the destination is this CTA's shared memory, the transaction bytes are counted on the mbarrier at
 // `cluster_bar` (a shared::cluster address, normally the leader CTA's barrier)
