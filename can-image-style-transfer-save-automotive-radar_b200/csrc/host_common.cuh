@@ -321,9 +321,11 @@ inline int promote_steps() {
 }
 // Forward convolutions: taps per accumulation chain inside a 64-channel chunk (chains never cross a chunk). Draining a
 // 128x128 fp32 accumulator takes ~1000 cycles of tensor-memory read bandwidth, the 12 MMAs of a k-step 768 cycles as a CTA
-// pair (1032 single-CTA): one chain per tap is drain-bound in pair mode. Measured (profiles/r01_promote_fwd_ab.log): chains
-// of 1 / 2 / 3 / 5 taps give a forward rel-L2 error of 1.5 / 2.0 / 2.7 / 3.7e-7 against fp64 and a 512^2 closure of
-// 1.70 / 1.52 / 1.47 / 1.45 ms; 3 taps (three chains per chunk) is the default for CTA pairs, 1 for the single-CTA kernel.
+// pair (1032 single-CTA), so short chains cost more as a pair. Measured (profiles/r01_promote_fwd_ab.log, second table):
+// chains of 1 / 2 / 3 / 5 taps give a forward rel-L2 error of 1.5 / 2.0 / 2.7 / 3.7e-7 against fp64 and a 512^2 closure of
+// 1.331 / 1.304 / 1.294 / 1.296 ms; 3 taps (three chains per chunk) is the default for CTA pairs, 1 for the single-CTA
+// kernel. On the parity points of tests/test_closure_gpu.py the image gradient is as close to fp64 with 3 taps as with 1
+// (its error is set by ReLU / pool mask flips, and stays at or below the reference's own fp32-vs-fp64 error).
 // IST_B200_PROMOTE_FWD overrides.
 inline int promote_steps_fwd() {
     static int v = 0;
