@@ -599,7 +599,7 @@ struct GramLayer {
     float weight;           // loss weight (STYLE_WEIGHTS[k], defaults.py:68)
     float bwd_coef;         // 2*w / (C^2 * H*W * s_act)
 };
-constexpr int GRAM_FIN_BLOCKS = 128;
+constexpr int GRAM_FIN_BLOCKS = 256;     // blocks per (layer, frame) of gram_reduce
 struct GramFinalizeParams {
     GramLayer L[8];
     int n_layers, NB, loss_stride;
@@ -614,17 +614,47 @@ gram_reduce_kernel(const GramFinalizeParams p) {
     float s = 0.f, mx = 0.f;
     pdl_trigger();
     pdl_wait();
-    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < CC; e += (size_t)gridDim.x * blockDim.x) {
-        float g = 0.f;
-        for (int sp = 0; sp < L.splits; ++sp) g += L.partial[((size_t)fr * L.splits + sp) * CC + e];
-        g *= L.g_scale;
-        if (L.g_out != nullptr) {
-            L.g_out[(size_t)fr * CC + e] = g;
-        } else {
-            const float d = g - __ldg(L.target + e);
-            L.diff[(size_t)fr * CC + e] = d;
-            s = fmaf(d, d, s);
-            mx = fmaxf(mx, fabsf(d));
+    // Every element sums its split partials in the fixed order sp = 0, 1, 2, ... . The loop is latency-bound (a thread owns
+    // few elements): two elements x four splits = eight independent loads are kept in flight.
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const float* pbase = L.partial + (size_t)fr * L.splits * CC;
+    for (size_t e0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e0 < CC; e0 += 2 * stride) {
+        const size_t e1 = e0 + stride;
+        const bool two = e1 < CC;
+        const float* p0 = pbase + e0;
+        const float* p1 = pbase + (two ? e1 : e0);
+        float g0 = 0.f, g1 = 0.f;
+        int sp = 0;
+        // layers with many splits (relu1_1: one split per SM) would otherwise walk a chain of splits / 4 dependent load rounds
+        for (; sp + 16 <= L.splits; sp += 16) {
+            float a[16], b[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { a[u] = __ldg(p0 + (size_t)(sp + u) * CC); b[u] = __ldg(p1 + (size_t)(sp + u) * CC); }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { g0 += a[u]; g1 += b[u]; }
+        }
+        for (; sp + 4 <= L.splits; sp += 4) {
+            const float a0 = __ldg(p0 + (size_t)sp * CC), a1 = __ldg(p0 + (size_t)(sp + 1) * CC);
+            const float a2 = __ldg(p0 + (size_t)(sp + 2) * CC), a3 = __ldg(p0 + (size_t)(sp + 3) * CC);
+            const float b0 = __ldg(p1 + (size_t)sp * CC), b1 = __ldg(p1 + (size_t)(sp + 1) * CC);
+            const float b2 = __ldg(p1 + (size_t)(sp + 2) * CC), b3 = __ldg(p1 + (size_t)(sp + 3) * CC);
+            g0 += a0; g0 += a1; g0 += a2; g0 += a3;
+            g1 += b0; g1 += b1; g1 += b2; g1 += b3;
+        }
+        for (; sp < L.splits; ++sp) { g0 += __ldg(p0 + (size_t)sp * CC); g1 += __ldg(p1 + (size_t)sp * CC); }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            const size_t e = u == 0 ? e0 : e1;
+            const float g = (u == 0 ? g0 : g1) * L.g_scale;
+            if (L.g_out != nullptr) {
+                L.g_out[(size_t)fr * CC + e] = g;
+            } else {
+                const float d = g - __ldg(L.target + e);
+                L.diff[(size_t)fr * CC + e] = d;
+                s = fmaf(d, d, s);
+                mx = fmaxf(mx, fabsf(d));
+            }
         }
     }
     if (L.g_out == nullptr) {
@@ -647,16 +677,29 @@ gram_dmat_kernel(const GramFinalizeParams p) {
     float mx = 0.f;
     pdl_trigger();
     pdl_wait();
-    for (int b = 0; b < GRAM_FIN_BLOCKS; ++b) mx = fmaxf(mx, L.blk_max[(size_t)fr * GRAM_FIN_BLOCKS + b]);
+    // every warp reduces the block maxima on its own (lane-strided loads + shuffles; max is order-independent)
+    static_assert(GRAM_FIN_BLOCKS % 32 == 0, "lane-strided reductions below");
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int b = 0; b < GRAM_FIN_BLOCKS; b += 32) mx = fmaxf(mx, L.blk_max[(size_t)fr * GRAM_FIN_BLOCKS + b + lane]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     int e2 = 0;
     if (mx > 0.f && isfinite(mx)) e2 = 13 - ilogbf(mx);
     const float sc = ldexpf(1.f, e2);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // sum of the block sums in a fixed order: lane l adds blocks [l * K, (l + 1) * K) in sequence, then a fixed shuffle tree
+        constexpr int K = GRAM_FIN_BLOCKS / 32;
         double s = 0.0;
-        for (int b = 0; b < GRAM_FIN_BLOCKS; ++b) s += (double)L.blk_sum[(size_t)fr * GRAM_FIN_BLOCKS + b];
+#pragma unroll
+        for (int b = 0; b < K; ++b) s += (double)L.blk_sum[(size_t)fr * GRAM_FIN_BLOCKS + lane * K + b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) {
         const float mean = (float)(s / (double)CC);
         *(L.loss_out + (size_t)fr * p.loss_stride) = L.weight * mean;
         L.alpha_out[fr] = L.bwd_coef * ldexpf(1.f, -e2);
+      }
     }
     const float* df = L.diff + (size_t)fr * CC;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < CC; e += (size_t)gridDim.x * blockDim.x) {
@@ -678,20 +721,28 @@ struct LossTotalParams {
     float c_scale[4];        // weight / (C*H*W * s_act^2)
     int n_content, c_blocks;
 };
-__global__ void loss_total_kernel(const LossTotalParams p) {
-    const int fr = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per frame (launch <<<NB, 32>>>): lane l adds the partials [l * K, (l + 1) * K) in sequence, a fixed shuffle tree adds
+// the lanes (deterministic order, no serial chain of dependent loads on the path between the forward and the backward pass).
+__global__ void __launch_bounds__(32) loss_total_kernel(const LossTotalParams p) {
+    const int fr = blockIdx.x, lane = threadIdx.x;
     pdl_trigger();
     pdl_wait();
     if (fr >= p.NB) return;
     float* L = p.losses + (size_t)fr * p.loss_stride;
     for (int k = 0; k < p.n_content; ++k) {
+        const int K = (p.c_blocks + 31) / 32;
         double s = 0.0;
-        for (int b = 0; b < p.c_blocks; ++b) s += (double)p.c_partial[k][(size_t)fr * p.c_blocks + b];
-        L[p.c_slot[k]] = (float)(s * (double)p.c_scale[k]);
+        for (int b = lane * K; b < (lane + 1) * K && b < p.c_blocks; ++b) s += (double)p.c_partial[k][(size_t)fr * p.c_blocks + b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) L[p.c_slot[k]] = (float)(s * (double)p.c_scale[k]);
     }
-    float t = 0.f;
-    for (int k = 0; k < p.n_losses; ++k) t += L[k];
-    L[p.n_losses] = t;
+    __syncwarp();
+    if (lane == 0) {
+        float t = 0.f;
+        for (int k = 0; k < p.n_losses; ++k) t += L[k];
+        L[p.n_losses] = t;
+    }
 }
 
 }  // namespace ist

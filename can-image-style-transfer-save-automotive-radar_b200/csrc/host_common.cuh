@@ -415,7 +415,15 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
             const int workers = conv_workers();
             const long long waves = (tiles_f + workers - 1) / workers;
             const double eff = (double)tiles_f / (double)(waves * workers);
-            const bool want = wsp->ws != nullptr && ch >= 2 && eff < 0.93 && tiles_f * ch < (1ll << 30);
+            // ... and only when the tensor work it saves outweighs the serial partial-tile exchange at the head CTA (one
+            // 64 KB partial through L2 per extra CTA of a tile, ~3000 cycles each; a k-step is ~770 cycles): tiny launches
+            // such as the 1x1 Gram backward of the deepest layer run faster as whole tiles on a few CTAs
+            const double ksteps_tile = (double)(p.Cin / 64) * p.taps + p.extra_chunks;
+            const double t_whole = (double)waves * ksteps_tile * 770.0;
+            const double share = (double)tiles_f / workers;                     // tiles per worker when split evenly
+            const double ways = share >= 1.0 ? 2.0 : ceil(1.0 / share);           // CTAs (pairs) that meet in one tile
+            const double t_split = share * ksteps_tile * 770.0 + (ways - 1.0) * 3000.0;
+            const bool want = wsp->ws != nullptr && ch >= 2 && eff < 0.93 && tiles_f * ch < (1ll << 30) && t_split < t_whole;
             p.sk_ws = want ? wsp->ws : nullptr;
             p.sk_flags = want ? wsp->flags : nullptr;
             const long long units = want ? tiles_f * ch : tiles_f;

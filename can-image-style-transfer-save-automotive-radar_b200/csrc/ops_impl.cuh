@@ -301,7 +301,7 @@ int ist_op_mse(const float* x, const float* tg, float weight, float* loss, float
     lt.losses = loss; lt.loss_stride = 2; lt.n_losses = 1; lt.NB = NB; lt.c_blocks = 64; lt.n_content = 1;
     lt.c_partial[0] = part; lt.c_slot[0] = 0;
     lt.c_scale[0] = (float)((double)weight / ((double)C * HW * kS * kS));
-    loss_total_kernel<<<(NB + 63) / 64, 64, 0, st>>>(lt);
+    loss_total_kernel<<<NB, 32, 0, st>>>(lt);
     IST_CUDA(cudaGetLastError());
     RouteParams r;
     memset(&r, 0, sizeof(r));

@@ -370,7 +370,7 @@ int run_loss_finalize(ist_plan* P, float* losses_dev, cudaStream_t st) {
         lt.c_scale[k] = (float)((double)L.content_w / ((double)L.C * L.H * L.W * kActScale * kActScale));
         lt.n_content++;
     }
-    IST_EWK("loss_total", 64.0 * P->NB, st, PDL_EW, loss_total_kernel, (P->NB + 63) / 64, 64, 0, lt);
+    IST_EWK("loss_total", 64.0 * P->NB, st, PDL_EW, loss_total_kernel, P->NB, 32, 0, lt);
     return IST_OK;
 }
 
