@@ -181,7 +181,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    long long* dbg = p.dbg_times != nullptr ? p.dbg_times + 8 * (size_t)blockIdx.x : nullptr;
+    long long* dbg = p.dbg_times != nullptr ? p.dbg_times + 16 * (size_t)blockIdx.x : nullptr;
+    // debug only: cycles one thread of a role spent waiting on a barrier, accumulated in dbg[slot] (slots 8-15)
+    long long wacc[3] = {0, 0, 0};          // per-thread accumulators, flushed by dbg_flush at the end of a role
+    auto timed_wait = [&](uint32_t bar, uint32_t parity, int k) {
+        if (dbg == nullptr) { mbar_wait(bar, parity); return; }
+        const long long t0 = clock64();
+        mbar_wait(bar, parity);
+        wacc[k] += clock64() - t0;
+    };
+    auto dbg_flush = [&](int slot0, int n) {
+        if (dbg != nullptr && (threadIdx.x & 31) == 0)
+            for (int k = 0; k < n; ++k) dbg[slot0 + k] = wacc[k];
+    };
     unsigned long long gt0 = 0;
     if (dbg != nullptr && threadIdx.x == 0) {
         dbg[0] = clock64();
@@ -295,7 +307,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 for (int cc = cbeg; cc < cend; ++cc) {
                     const bool ex = cc >= cchunks;
                     const int c64 = (ex ? cc - cchunks : cc) * 64;
-                    mbar_wait(aempty(as), aph ^ 1u);
+                    timed_wait(aempty(as), aph ^ 1u, 0);
                     const uint32_t sA = a_base + as * Cfg::A_STAGE;
                     if constexpr (PAIR) {
                         // the leader announces the bytes of both CTAs; each CTA's loads complete on the leader's barrier
@@ -314,7 +326,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     const int ntap = ex ? 1 : taps;
                     for (int tap = 0; tap < ntap; ++tap) {
                         const int bz = (p.b_frame || ex) ? fr : tap;
-                        mbar_wait(bempty(bs), bph ^ 1u);
+                        timed_wait(bempty(bs), bph ^ 1u, 1);
                         const uint32_t sB = b_base + bs * Cfg::B_STAGE;
                         if constexpr (PAIR) {
                             const uint32_t lbar = mapa_u32(bfull(bs), 0);
@@ -332,6 +344,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     }
                 }
             }
+            dbg_flush(13, 2);
         }
     } else if (warp == 1) {
       if (rank == 0) {
@@ -355,7 +368,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const int kit_seg = (mend > cbeg ? mend - cbeg : 0) * taps;
             int kit = 0;
             for (int cc = cbeg; cc < mend; ++cc) {
-                mbar_wait(afull(as), aph);
+                timed_wait(afull(as), aph, 2);
                 const uint32_t a_lo_stage = (a_base + as * Cfg::A_STAGE) >> 4;
                 for (int ky = 0; ky < kyn; ++ky) {
                     for (int kx = 0; kx < kyn; ++kx, ++kit) {
@@ -364,8 +377,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         // the stream-K ranges are cut (translation-invariant rounding)
                         const int in_chain = (ky * kyn + kx) % promote;
                         const bool chain_end = (in_chain == promote - 1) || last_tap;
-                        if (in_chain == 0) mbar_wait(mempty(mb), mph ^ 1u);
-                        mbar_wait(bfull(bs), bph);
+                        if (in_chain == 0) timed_wait(mempty(mb), mph ^ 1u, 0);
+                        timed_wait(bfull(bs), bph, 1);
                         tc_fence_after();
                         if (elect_one()) {
                             if (dbg != nullptr && first) dbg[2] = clock64();
@@ -402,6 +415,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
             }
         }
+        dbg_flush(8, 3);
       }
     } else if (warp == 6) {
         // ------------------------------ MMA issuer 2: hi*lo + lo*hi cross terms, fused Gram k-steps ----------------------
@@ -420,19 +434,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 const uint32_t xph = xsingle ? (scount & 1u) : ((scount >> 1) & 1u);
                 const uint32_t d_cross = tmem_base + (uint32_t)Cfg::CROSS_COL + xa * N_TILE;
                 const uint32_t d_gram = tmem_base + (uint32_t)Cfg::GRAM_COL + xa * N_TILE;
-                mbar_wait(xempty(xa), xph ^ 1u);
+                timed_wait(xempty(xa), xph ^ 1u, 1);
                 tc_fence_after();
                 int kit = 0, xc = 0;
                 for (int cc = cbeg; cc < cend; ++cc) {
                     const bool ex = cc >= cchunks;
                     const bool last_chunk = (cc == cend - 1);
-                    mbar_wait(afull(as), aph);
+                    timed_wait(afull(as), aph, 0);
                     const uint32_t a_lo_stage = (a_base + as * Cfg::A_STAGE) >> 4;
                     if (!ex) {
                         for (int ky = 0; ky < kyn; ++ky) {
                             for (int kx = 0; kx < kyn; ++kx, ++kit) {
                                 const bool last_tap = (ky == kyn - 1 && kx == kyn - 1);
-                                mbar_wait(bfull(bs), bph);
+                                timed_wait(bfull(bs), bph, 0);
                                 tc_fence_after();
                                 if (elect_one()) {
                                     const uint32_t a_lo = a_lo_stage + (uint32_t)((ky * Cfg::PW + kx) * 8);
@@ -475,6 +489,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 }
                 ++scount;
             }
+            dbg_flush(11, 2);
         }
     } else {
         // ------------------------------------------- promotion + epilogue ---------------------------------------------
@@ -503,7 +518,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
             for (int j = 0; j < NH; ++j) acc[j] = 0.f;
             for (int ch = 0; ch < nchains; ++ch) {
-                mbar_wait(mfull(mb), mph);
+                timed_wait(mfull(mb), mph, 0);
                 tc_fence_after();
 #pragma unroll
                 for (int c0 = 0; c0 < NH; c0 += 32) {
@@ -668,6 +683,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
         // the staging buffers must have been read before the CTA may exit; the global writes themselves complete with the grid
         if (p.use_tma_store && storer) tma_store_wait_read();
+        if (warp == 2) dbg_flush(15, 1);
     }
 #undef IST_FOR_SEGMENTS
 

@@ -283,20 +283,27 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
         // phase stamps per CTA: 0 entry, 1 setup done, 2 first MMA issued, 3 last MMA of the last tile issued,
         // 4 last tile's accumulators in registers, 5 last tile stored, 6 exit
         static long long* dbuf = nullptr;
-        if (dbuf == nullptr) IST_CUDA(cudaMalloc(&dbuf, sizeof(long long) * 8 * 1024));
-        IST_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(long long) * 8 * 1024, st));
+        if (dbuf == nullptr) IST_CUDA(cudaMalloc(&dbuf, sizeof(long long) * 16 * 1024));
+        IST_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(long long) * 16 * 1024, st));
         ConvParams q = p;
         q.dbg_times = dbuf;
         IST_CUDA(launch_kc(conv_halo_kernel<N_TILE, PAIR>, dim3(grid), dim3(HaloCfg<N_TILE, PAIR>::THREADS), HaloCfg<N_TILE, PAIR>::SMEM_BYTES, st, 0, PAIR ? 2 : 1, a_hi, a_lo, b_hi, b_lo, o_hi, o_lo, f_hi, f_lo, d_hi, d_lo, q));
         IST_CUDA(cudaStreamSynchronize(st));
-        std::vector<long long> h(8 * (size_t)grid);
-        IST_CUDA(cudaMemcpy(h.data(), dbuf, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost));
+        std::vector<long long> h(16 * (size_t)grid);
+        IST_CUDA(cudaMemcpy(h.data(), dbuf, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost));
         double sum[7] = {0, 0, 0, 0, 0, 0, 0};
         double ns = 0;
+        double wsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // barrier wait cycles per role (leader CTAs for the issuers)
+        int nlead = 0;
         for (int c = 0; c < grid; ++c) {
-            for (int k = 1; k < 7; ++k) sum[k] += (double)(h[8 * c + k] - h[8 * c]);
-            ns += (double)h[8 * c + 7];
+            for (int k = 1; k < 7; ++k) sum[k] += (double)(h[16 * c + k] - h[16 * c]);
+            ns += (double)h[16 * c + 7];
+            const bool lead = !PAIR || (c % 2 == 0);
+            if (lead) ++nlead;
+            for (int k = 8; k < 16; ++k) if (lead || k == 13 || k == 14 || k == 15) wsum[k - 8] += (double)h[16 * c + k];
         }
+        fprintf(stderr, "[dbg-wait] avg cycles waiting | issuer1: acc-empty %.0f B-full %.0f A-full %.0f | issuer2: operands %.0f cross-empty %.0f | producer: A-empty %.0f B-empty %.0f | epilogue warp 2: acc-full %.0f\n",
+                wsum[0] / nlead, wsum[1] / nlead, wsum[2] / nlead, wsum[3] / nlead, wsum[4] / nlead, wsum[5] / grid, wsum[6] / grid, wsum[7] / grid);
         fprintf(stderr, "[dbg] conv %dx%d %d->%d taps %d passes %d promote %d grid %d tiles %d | avg clk since entry: setup %.0f first_mma %.0f last_issue %.0f acc_read %.0f stored %.0f exit %.0f | %.1f us -> SM clock %.0f MHz\n",
                 p.H, p.W, p.Cin, p.Cout, p.taps, p.passes, p.promote, grid, total, sum[1] / grid, sum[2] / grid, sum[3] / grid,
                 sum[4] / grid, sum[5] / grid, sum[6] / grid, ns / grid * 1e-3, sum[6] / ns * 1e3);
