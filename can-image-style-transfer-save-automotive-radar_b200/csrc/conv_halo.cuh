@@ -517,7 +517,44 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             float acc[NH];
 #pragma unroll
             for (int j = 0; j < NH; ++j) acc[j] = 0.f;
+            const int slot = fcount & 1;                  // partial tiles are double-buffered over the frames a CTA walks
+            // Head of a tile whose remaining chunks belong to the following workers of this frame group: their partial tiles
+            // (published at the START of their ranges) are added in worker order. The 64 KB read through L2 happens `nmain`
+            // chains before the end of this segment: the remaining chains fit in the accumulator ring, so the tensor core
+            // finishes the segment while the partials are fetched (and while a late partial is waited for). The position of
+            // the additions in the sum depends on the geometry only: results stay run-to-run identical.
+            bool partials_done = !(p.sk_ws != nullptr && cbeg == 0 && cend < CH);
+            auto add_partials = [&]() {
+                int covered = cend;
+                for (int ol = lid + 1; covered < CH; ++ol) {
+                    const long long Gt = (long long)tiles_f * CH;
+                    const int ob = (int)(Gt * ol / cpf), oe = (int)(Gt * (ol + 1) / cpf);
+                    const int olen = (oe - ob) < (CH - covered) ? (oe - ob) : (CH - covered);
+                    const int oc = PAIR ? 2 * (fgroup * cpf + ol) + (int)rank : fgroup * cpf + ol;      // same-rank CTA of worker ol
+                    int* flag = p.sk_flags + 2 * oc + slot;
+                    if (threadIdx.x == 64) {
+                        int v = 0;
+                        uint32_t spins = 0;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                            if (++spins > (1u << 26)) __trap();
+                        } while (v == 0);
+                    }
+                    bar_all();
+                    const float* ws = p.sk_ws + (size_t)(2 * oc + slot) * (128 * N_TILE) + (size_t)col0 * 128;
+#pragma unroll
+                    for (int j = 0; j < NH; ++j) acc[j] += __ldcg(ws + j * 128 + m);
+                    bar_all();
+                    if (threadIdx.x == 64) {
+                        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(0) : "memory");
+                    }
+                    covered += olen;
+                }
+                partials_done = true;
+            };
+            const int gather_at = nchains > (int)nmain ? nchains - (int)nmain : 0;
             for (int ch = 0; ch < nchains; ++ch) {
+                if (!partials_done && ch == gather_at) add_partials();
                 timed_wait(mfull(mb), mph, 0);
                 tc_fence_after();
 #pragma unroll
@@ -570,7 +607,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
             ++scount;
             if (dbg != nullptr && threadIdx.x == 64) dbg[4] = clock64();
-            const int slot = fcount & 1;                  // partial tiles are double-buffered over the frames a CTA walks
             if (cbeg != 0) {
                 // partial tile of a segment that starts inside a tile: hand it to the CTA that holds the tile's head
                 int* flag = p.sk_flags + 2 * blockIdx.x + slot;
@@ -593,35 +629,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 }
                 continue;
             }
-            if (cend < CH) {
-                // head of a tile whose remaining chunks belong to the following CTAs of this frame group: add their partials
-                // in CTA order
-                int covered = cend;
-                for (int ol = lid + 1; covered < CH; ++ol) {
-                    const long long Gt = (long long)tiles_f * CH;
-                    const int ob = (int)(Gt * ol / cpf), oe = (int)(Gt * (ol + 1) / cpf);
-                    const int olen = (oe - ob) < (CH - covered) ? (oe - ob) : (CH - covered);
-                    const int oc = PAIR ? 2 * (fgroup * cpf + ol) + (int)rank : fgroup * cpf + ol;      // same-rank CTA of worker ol
-                    int* flag = p.sk_flags + 2 * oc + slot;
-                    if (threadIdx.x == 64) {
-                        int v = 0;
-                        uint32_t spins = 0;
-                        do {
-                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-                            if (++spins > (1u << 26)) __trap();
-                        } while (v == 0);
-                    }
-                    bar_all();
-                    const float* ws = p.sk_ws + (size_t)(2 * oc + slot) * (128 * N_TILE) + (size_t)col0 * 128;
-#pragma unroll
-                    for (int j = 0; j < NH; ++j) acc[j] += __ldcg(ws + j * 128 + m);
-                    bar_all();
-                    if (threadIdx.x == 64) {
-                        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(0) : "memory");
-                    }
-                    covered += olen;
-                }
-            }
+            if (!partials_done) add_partials();            // segments without main chains
             float alpha = p.alpha;
             if (p.alpha_dev != nullptr) alpha *= __ldg(p.alpha_dev + (size_t)p.alpha_stride * fr);
             const int gx = tx * Cfg::TW + (m % Cfg::TW), gy = ty * Cfg::TH + (m / Cfg::TW);
