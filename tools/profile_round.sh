@@ -15,6 +15,6 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,
     --clock-control none -k regex:conv_halo -s 96 -c 25 --csv --log-file $O/${TAG}_ncu_conv_25launches_metrics.csv \
     python tools/gpu_closure_bench.py 512 1 > $O/${TAG}_ncu_conv25.log 2>&1
 # full capture of one conv4_2-shaped forward launch (512 -> 512 channels at 64 x 64)
-ncu --set full --clock-control none --import-source on -k regex:conv_halo -s 3 -c 1 -o $O/${TAG}_conv_pair_c42 \
+ncu --set full --clock-control none --import-source on -k regex:conv_halo -s 1 -c 1 -o $O/${TAG}_conv_pair_c42 \
     python tools/gpu_conv_probe.py 512,512,64 > $O/${TAG}_ncu_full.log 2>&1
 ls -la $O | grep ${TAG}
