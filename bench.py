@@ -36,7 +36,7 @@ def config_dict(n_gpus):
         "size": SIZE, "evals_per_step": EVALS_PER_FRAME, "frames_per_step": n_gpus,
         "weights": "synthetic Kaiming-normal VGG19 (vgg_conv.pth unavailable offline), seed 0",
         "style_layers": "relu1_1..relu5_1", "content_layers": "relu4_2", "lbfgs": "torch defaults (lr 1, max_iter 20, history 100, no line search)",
-        "precision": "fp16 hi/lo split operands (3 tcgen05 MMAs per product) forward, bf16 hi/lo split data-gradient, fp32 accumulation promoted to registers every k-step",
+        "precision": "fp16 hi/lo split operands (3 tcgen05 MMAs per product) forward, bf16 hi/lo split data-gradient, fp32 accumulation promoted from tensor memory to registers every 3 taps forward (CTA pairs, tcgen05 cta_group::2), every 64-channel chunk backward",
         "l2": "working set per step (~0.35 GB activations + 0.63 GB L-BFGS history) exceeds the 126 MB L2; no explicit flush",
         "parallelism": "dp%d (independent frames, one end-of-run gather)" % n_gpus,
     }
