@@ -30,8 +30,10 @@ struct GramParams {
 
 struct GramCfg {
     static constexpr int T_BYTES = 128 * 128;            // [64 pixels][128 channels] x 2 B, as two 8 KB channel groups
-    static constexpr int STAGE_BYTES = 4 * T_BYTES;      // A_hi, A_lo, B_hi, B_lo
-    static constexpr int STAGES = 3;
+    static constexpr int STAGE_BYTES = 4 * T_BYTES;      // largest stage: A_hi, A_lo, B_hi, B_lo of an off-diagonal 128-wide tile
+    static constexpr int STAGES = 3;                     // stages of that size; smaller stages get more (see RING_BYTES)
+    static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int MAX_STAGES = 8;                 // barrier slots
     static constexpr int TMEM_COLS = 512;                // main[2] @0,128; cross @256
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
 };
@@ -40,10 +42,9 @@ __global__ void __launch_bounds__(192, 1)
 gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                  const GramParams p) {
     using Cfg = GramCfg;
-    constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    const uint32_t bar_base = smem_base + Cfg::RING_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
     auto mfull_bar = [&](uint32_t b) { return bar_base + 128u + 8u * b; };
@@ -51,7 +52,7 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const uint32_t xfull_bar = bar_base + 160u;
     const uint32_t tmem_slot = bar_base + 192u;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
-        smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * Cfg::STAGE_BYTES + 192);
+        smem_raw + (smem_base - smem_u32(smem_raw)) + Cfg::RING_BYTES + 192);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -76,12 +77,20 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const int groups_a = (p.C >= 128) ? 2 : 1;           // 64-channel groups actually loaded per operand
     const int groups_b = p.n_tile >> 6;
     const int promote = p.promote < 1 ? 1 : p.promote;
+    // Stage layout [A_hi][A_lo][B_hi][B_lo], every plane `plane_bytes`; diagonal tiles load no B, C = 64 has 8 KB planes. The
+    // 192 KB ring is cut into as many stages as fit (up to 8): a C = 64 / C = 128 layer is a pure HBM stream (16 / 32 KB per
+    // 64-pixel chunk), and with three stages in flight it ran at the DRAM latency (2.0-2.6 TB/s) instead of the bandwidth.
+    const uint32_t plane_bytes = (uint32_t)groups_a * 8192u;
+    const uint32_t stage_bytes = (uint32_t)((p.passes == 3) ? 2 : 1) * (diag ? 1u : 2u) * plane_bytes;
+    int nstages = (int)(Cfg::RING_BYTES / stage_bytes);
+    if (nstages > Cfg::MAX_STAGES) nstages = Cfg::MAX_STAGES;
+    const uint32_t b_off = ((p.passes == 3) ? 2u : 1u) * plane_bytes;      // B planes follow the A planes
 
     pdl_trigger();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_hi);
         if (p.passes == 3) tma_prefetch_desc(&tm_lo);
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < Cfg::MAX_STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
@@ -108,18 +117,18 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
             for (int kit = 0; kit < kiters; ++kit) {
                 const int pix = (c_begin + kit) * 64;
                 mbar_wait(empty_bar(stage), phase ^ 1u);
-                const uint32_t s0 = smem_base + stage * Cfg::STAGE_BYTES;
+                const uint32_t s0 = smem_base + stage * stage_bytes;
                 mbar_arrive_expect_tx(full_bar(stage), tx);
                 for (int pl = 0; pl < planes; ++pl) {
                     const CUtensorMap* tm = pl == 0 ? &tm_hi : &tm_lo;
                     for (int g = 0; g < groups_a; ++g)
-                        tma_load_3d(s0 + pl * Cfg::T_BYTES + g * 8192, tm, full_bar(stage), mt * 128 + g * 64, pix, fr);
+                        tma_load_3d(s0 + pl * plane_bytes + g * 8192, tm, full_bar(stage), mt * 128 + g * 64, pix, fr);
                     if (!diag)
                         for (int g = 0; g < groups_b; ++g)
-                            tma_load_3d(s0 + (2 + pl) * Cfg::T_BYTES + g * 8192, tm, full_bar(stage),
+                            tma_load_3d(s0 + b_off + pl * plane_bytes + g * 8192, tm, full_bar(stage),
                                         nt * 128 + g * 64, pix, fr);
                 }
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                if (++stage == nstages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -138,8 +147,8 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
             tc_fence_after();
             if (elect_one()) {
                 // MN-major SW128 descriptors: low word = start >> 4 | (LBO = 8192 B) >> 4 << 16, constant high word
-                const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
-                const uint32_t sB = diag ? sA : sA + 2 * Cfg::T_BYTES;
+                const uint32_t sA = smem_base + stage * stage_bytes;
+                const uint32_t sB = diag ? sA : sA + b_off;
                 const uint32_t a_lo = (sA >> 4) | ((8192u >> 4) << 16);
                 const uint32_t b_lo = (sB >> 4) | ((8192u >> 4) << 16);
                 const uint32_t hi_w = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -153,9 +162,9 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
                 if (split3) {
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
-                        umma_f16_lh(d_cross, a_lo + k4 * 128, hi_w, b_lo + (Cfg::T_BYTES >> 4) + k4 * 128, hi_w, idesc,
+                        umma_f16_lh(d_cross, a_lo + k4 * 128, hi_w, b_lo + (plane_bytes >> 4) + k4 * 128, hi_w, idesc,
                                     (kit | k4) != 0 ? 1u : 0u);
-                        umma_f16_lh(d_cross, a_lo + (Cfg::T_BYTES >> 4) + k4 * 128, hi_w, b_lo + k4 * 128, hi_w, idesc, 1u);
+                        umma_f16_lh(d_cross, a_lo + (plane_bytes >> 4) + k4 * 128, hi_w, b_lo + k4 * 128, hi_w, idesc, 1u);
                     }
                 }
                 umma_commit(empty_bar(stage));
@@ -163,7 +172,7 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
             }
             __syncwarp();
             if (in_chain == promote - 1 || kit == kiters - 1) ++mcount;
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
     } else {
         const int quad = warp & 3;
