@@ -16,6 +16,7 @@
 #include "conv_halo.cuh"
 #include "elementwise.cuh"
 #include "gram.cuh"
+#include "conv_first_tc.cuh"
 
 namespace ist {
 
@@ -463,6 +464,38 @@ inline int launch_conv_first_dgrad(cudaStream_t st, const uint16_t* g_hi, const 
     launch_pre("conv_first_dgrad", 2.0 * px * 64 * 27, px * (12.0 + 256.0), st);
     dim3 grid((W + CFD_TX - 1) / CFD_TX, (H + CFD_TY - 1) / CFD_TY, NB);
     IST_CUDA(launch_k(conv_first_dgrad_kernel<64>, grid, dim3(256), CFD_SMEM, st, pdl ? PDL_EW : 0, g_hi, g_lo, w, grad, NB, H, W));
+    launch_post(st);
+    return IST_OK;
+}
+
+// conv1_1 data-gradient on the tensor cores (conv_first_tc.cuh). IST_B200_CFD=cuda selects the CUDA-core kernel.
+inline int cfd_use_tc() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("IST_B200_CFD");
+        v = (e != nullptr && strcmp(e, "cuda") == 0) ? 0 : 1;
+    }
+    return v;
+}
+inline int launch_conv_first_dgrad_tc(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                                      const CUtensorMap& b_lo, float* grad, int NB, int H, int W, bool pdl) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        IST_CUDA(cudaFuncSetAttribute(conv_first_dgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CfdTcCfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    CfdTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.NB = NB; p.H = H; p.W = W;
+    p.tiles_x = (W + CfdTcCfg::TW - 1) / CfdTcCfg::TW;
+    p.tiles_y = (H + CfdTcCfg::TH - 1) / CfdTcCfg::TH;
+    p.grad = grad;
+    p.idesc = umma_idesc_f16(UMMA_FMT_BF16, 128, CfdTcCfg::N_PAD, 0, 0);
+    const long long total = (long long)NB * p.tiles_x * p.tiles_y;
+    const int grid = total < num_sms() ? (int)total : num_sms();
+    const double px = (double)NB * H * W;
+    launch_pre("conv_first_dgrad", 2.0 * px * 64 * 27, px * (12.0 + 256.0), st);
+    IST_CUDA(launch_k(conv_first_dgrad_tc_kernel, dim3(grid), dim3(224), CfdTcCfg::SMEM_BYTES, st, pdl ? PDL_TENSOR : 0, a_hi, a_lo, b_hi, b_lo, p));
     launch_post(st);
     return IST_OK;
 }

@@ -312,7 +312,10 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
         }
     }
     Layer& L0 = P->layers[0];
-    IST_TRY(launch_conv_first_dgrad(st, L0.dY.hi, L0.dY.lo, L0.w_f32, grad, NB, L0.H, L0.W, true));
+    if (cfd_use_tc() && conv_impl_halo() && L0.cout == 64)
+        IST_TRY(launch_conv_first_dgrad_tc(st, L0.mG_hi, L0.mG_lo, L0.mBd_hi, L0.mBd_lo, grad, NB, L0.H, L0.W, true));
+    else
+        IST_TRY(launch_conv_first_dgrad(st, L0.dY.hi, L0.dY.lo, L0.w_f32, grad, NB, L0.H, L0.W, true));
     return IST_OK;
 }
 
@@ -482,6 +485,13 @@ int ist_plan_create(ist_plan** out, int n_layers, const ist_layer_desc* layers, 
             rc = P->mem.alloc(&L.w_f32, (size_t)L.cout * L.cin * 9);
             if (rc == IST_OK) rc = map_act(&L.mGo_hi, L.dY.hi, batch, L.H, L.W, L.cout, 1);
             if (rc == IST_OK) rc = map_act(&L.mGo_lo, L.dY.lo, batch, L.H, L.W, L.cout, 1);
+            // tensor-core data-gradient of the first conv (conv_first_tc.cuh): dY halo maps, weights as [tap][16][64] planes
+            if (rc == IST_OK) rc = P->mem.alloc(&L.wd_hi, (size_t)9 * CfdTcCfg::N_PAD * 64);
+            if (rc == IST_OK) rc = P->mem.alloc(&L.wd_lo, (size_t)9 * CfdTcCfg::N_PAD * 64);
+            if (rc == IST_OK) rc = map_b(&L.mBd_hi, L.wd_hi, 9, CfdTcCfg::N_PAD, 64, CfdTcCfg::N_PAD);
+            if (rc == IST_OK) rc = map_b(&L.mBd_lo, L.wd_lo, 9, CfdTcCfg::N_PAD, 64, CfdTcCfg::N_PAD);
+            if (rc == IST_OK) rc = map_act(&L.mG_hi, L.dY.hi, batch, L.H, L.W, L.cout, 9);
+            if (rc == IST_OK) rc = map_act(&L.mG_lo, L.dY.lo, batch, L.H, L.W, L.cout, 9);
             continue;
         }
         const size_t wn = (size_t)L.cout * L.cin * 9;
@@ -530,6 +540,10 @@ int ist_plan_set_weights(ist_plan* P, int conv_index, const float* w_dev, const 
         IST_CUDA(cudaMemcpyAsync(L.bias, b_dev, L.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
         if (L.conv_index == 0) {
             IST_CUDA(cudaMemcpyAsync(L.w_f32, w_dev, wn * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            if (L.cout == 64 && L.wd_hi != nullptr) {
+                cfd_tc_weight_repack_kernel<<<36, 256, 0, st>>>(w_dev, L.wd_hi, L.wd_lo);
+                IST_CUDA(cudaGetLastError());
+            }
         } else {
             // power-of-two scale so the largest |w| lands in [2^13, 2^14): both fp16 halves stay normal
             std::vector<float> hw(wn);
