@@ -618,6 +618,50 @@ gram_reduce_kernel(const GramFinalizeParams p) {
     // few elements): two elements x four splits = eight independent loads are kept in flight.
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const float* pbase = L.partial + (size_t)fr * L.splits * CC;
+    if (L.splits >= 32) {
+        // Narrow layers (C = 64 / 128: one split per SM, few elements): four lanes share an element, each adds a contiguous
+        // quarter of the splits in order, a fixed two-step shuffle tree adds the quarters. A single thread per element would
+        // walk splits / 16 dependent rounds of loads through L2.
+        const int lane = threadIdx.x & 31, part = lane & 3, q = lane >> 2;
+        const int per = (L.splits + 3) >> 2;
+        const int sp0 = part * per, sp1 = (sp0 + per < L.splits) ? sp0 + per : L.splits;
+        const size_t nquads = stride >> 2;
+        for (size_t eb = ((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 2) - q; eb < CC; eb += nquads) {
+            const size_t e = eb + q;
+            const bool ok = e < CC;
+            float g = 0.f;
+            if (ok) {
+                const float* p0 = pbase + e;
+                int sp = sp0;
+                for (; sp + 16 <= sp1; sp += 16) {
+                    float a[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) a[u] = __ldg(p0 + (size_t)(sp + u) * CC);
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) g += a[u];
+                }
+                for (; sp + 4 <= sp1; sp += 4) {
+                    const float a0 = __ldg(p0 + (size_t)sp * CC), a1 = __ldg(p0 + (size_t)(sp + 1) * CC);
+                    const float a2 = __ldg(p0 + (size_t)(sp + 2) * CC), a3 = __ldg(p0 + (size_t)(sp + 3) * CC);
+                    g += a0; g += a1; g += a2; g += a3;
+                }
+                for (; sp < sp1; ++sp) g += __ldg(p0 + (size_t)sp * CC);
+            }
+            g += __shfl_xor_sync(0xffffffffu, g, 1);
+            g += __shfl_xor_sync(0xffffffffu, g, 2);
+            if (ok && part == 0) {
+                g *= L.g_scale;
+                if (L.g_out != nullptr) {
+                    L.g_out[(size_t)fr * CC + e] = g;
+                } else {
+                    const float d = g - __ldg(L.target + e);
+                    L.diff[(size_t)fr * CC + e] = d;
+                    s = fmaf(d, d, s);
+                    mx = fmaxf(mx, fabsf(d));
+                }
+            }
+        }
+    } else
     for (size_t e0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e0 < CC; e0 += 2 * stride) {
         const size_t e1 = e0 + stride;
         const bool two = e1 < CC;
@@ -633,15 +677,18 @@ gram_reduce_kernel(const GramFinalizeParams p) {
 #pragma unroll
             for (int u = 0; u < 16; ++u) { g0 += a[u]; g1 += b[u]; }
         }
-        for (; sp + 4 <= L.splits; sp += 4) {
-            const float a0 = __ldg(p0 + (size_t)sp * CC), a1 = __ldg(p0 + (size_t)(sp + 1) * CC);
-            const float a2 = __ldg(p0 + (size_t)(sp + 2) * CC), a3 = __ldg(p0 + (size_t)(sp + 3) * CC);
-            const float b0 = __ldg(p1 + (size_t)sp * CC), b1 = __ldg(p1 + (size_t)(sp + 1) * CC);
-            const float b2 = __ldg(p1 + (size_t)(sp + 2) * CC), b3 = __ldg(p1 + (size_t)(sp + 3) * CC);
-            g0 += a0; g0 += a1; g0 += a2; g0 += a3;
-            g1 += b0; g1 += b1; g1 += b2; g1 += b3;
+        // remaining splits (fewer than 16): batches of 8 predicated loads (adding 0.f leaves the sum unchanged)
+        for (; sp < L.splits; sp += 8) {
+            float a[8], b[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool in = sp + u < L.splits;
+                a[u] = in ? __ldg(p0 + (size_t)(sp + u) * CC) : 0.f;
+                b[u] = in ? __ldg(p1 + (size_t)(sp + u) * CC) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { g0 += a[u]; g1 += b[u]; }
         }
-        for (; sp < L.splits; ++sp) { g0 += __ldg(p0 + (size_t)sp * CC); g1 += __ldg(p1 + (size_t)sp * CC); }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             if (u == 1 && !two) break;
