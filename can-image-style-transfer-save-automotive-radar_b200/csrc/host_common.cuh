@@ -17,6 +17,7 @@
 #include "elementwise.cuh"
 #include "gram.cuh"
 #include "conv_first_tc.cuh"
+#include "conv_first_fwd_tc.cuh"
 
 namespace ist {
 
@@ -468,6 +469,37 @@ inline int launch_conv_first_dgrad(cudaStream_t st, const uint16_t* g_hi, const 
     return IST_OK;
 }
 
+// conv1_1 forward on the tensor cores (conv_first_fwd_tc.cuh): IST_B200_CFF=tc | cuda.
+inline int cff_use_tc() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("IST_B200_CFF");
+        v = (e != nullptr && strcmp(e, "tc") == 0) ? 1 : 0;
+    }
+    return v;
+}
+inline int launch_conv_first_fwd_tc(cudaStream_t st, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const float* x, const float* w,
+                                    const float* bias, int NB, int H, int W, float out_scale, int pdl) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        IST_CUDA(cudaFuncSetAttribute(conv_first_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CffTcCfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    CffTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.NB = NB; p.H = H; p.W = W;
+    p.tiles_x = (W + CffTcCfg::TW - 1) / CffTcCfg::TW;
+    p.tiles_y = (H + CffTcCfg::TH - 1) / CffTcCfg::TH;
+    p.x = x; p.w = w; p.bias = bias; p.out_scale = out_scale;
+    p.idesc = umma_idesc_f16(UMMA_FMT_F16, 128, 64, 0, 0);
+    const long long total = (long long)NB * p.tiles_x * p.tiles_y;
+    const int grid = total < num_sms() ? (int)total : num_sms();
+    const double px = (double)NB * H * W;
+    launch_pre("conv_first_fwd", 2.0 * px * 64 * 27, px * (12.0 + 256.0), st);
+    IST_CUDA(launch_k(conv_first_fwd_tc_kernel, dim3(grid), dim3(CffTcCfg::THREADS), CffTcCfg::SMEM_BYTES, st, pdl, o_hi, o_lo, p));
+    launch_post(st);
+    return IST_OK;
+}
 // conv1_1 data-gradient on the tensor cores (conv_first_tc.cuh). IST_B200_CFD=cuda selects the CUDA-core kernel.
 inline int cfd_use_tc() {
     static int v = -1;

@@ -113,7 +113,10 @@ int run_forward(ist_plan* P, const float* x, int upto, cudaStream_t st, int from
         Layer& L = P->layers[l];
         if (L.kind == IST_LAYER_CONV3X3_RELU) {
             if (!L.has_weights) return fail(IST_ERR_STATE, "conv layer %d has no weights (ist_plan_set_weights)", l);
-            if (l == 0) {
+            if (l == 0 && cff_use_tc() && conv_impl_halo()) {
+                IST_TRY(launch_conv_first_fwd_tc(st, L.mO_hi, L.mO_lo, x, L.w_f32, L.bias, P->NB, L.H, L.W, kActScale,
+                                                 P->pdl_first ? PDL_TENSOR : 0));
+            } else if (l == 0) {
                 const size_t px = (size_t)P->NB * L.H * L.W;
                 launch_pre("conv_first_fwd", 2.0 * px * 64 * 27, px * (12.0 + 256.0), st);
                 IST_CUDA(launch_k(conv_first_fwd_kernel<64>, dim3((L.W + CFF_TX - 1) / CFF_TX, (L.H + CFF_TY - 1) / CFF_TY, P->NB), dim3(256), 0, st,
@@ -485,6 +488,8 @@ int ist_plan_create(ist_plan** out, int n_layers, const ist_layer_desc* layers, 
             rc = P->mem.alloc(&L.w_f32, (size_t)L.cout * L.cin * 9);
             if (rc == IST_OK) rc = map_act(&L.mGo_hi, L.dY.hi, batch, L.H, L.W, L.cout, 1);
             if (rc == IST_OK) rc = map_act(&L.mGo_lo, L.dY.lo, batch, L.H, L.W, L.cout, 1);
+            if (rc == IST_OK) rc = map_act(&L.mO_hi, L.out.hi, batch, L.H, L.W, L.cout, 1);      // TMA-store maps of the tensor-core forward
+            if (rc == IST_OK) rc = map_act(&L.mO_lo, L.out.lo, batch, L.H, L.W, L.cout, 1);
             // tensor-core data-gradient of the first conv (conv_first_tc.cuh): dY halo maps, weights as [tap][16][64] planes
             if (rc == IST_OK) rc = P->mem.alloc(&L.wd_hi, (size_t)9 * CfdTcCfg::N_PAD * 64);
             if (rc == IST_OK) rc = P->mem.alloc(&L.wd_lo, (size_t)9 * CfdTcCfg::N_PAD * 64);
