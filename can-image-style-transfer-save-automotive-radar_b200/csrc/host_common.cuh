@@ -469,12 +469,12 @@ inline int launch_conv_first_dgrad(cudaStream_t st, const uint16_t* g_hi, const 
     return IST_OK;
 }
 
-// conv1_1 forward on the tensor cores (conv_first_fwd_tc.cuh): IST_B200_CFF=tc | cuda.
+// conv1_1 forward on the tensor cores (conv_first_fwd_tc.cuh). IST_B200_CFF=cuda selects the CUDA-core kernel.
 inline int cff_use_tc() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("IST_B200_CFF");
-        v = (e != nullptr && strcmp(e, "tc") == 0) ? 1 : 0;
+        v = (e != nullptr && strcmp(e, "cuda") == 0) ? 0 : 1;
     }
     return v;
 }
