@@ -44,7 +44,8 @@ struct LbFrame {
 
 struct LbParams {
     int NB, n, m;                 // frames, elements per frame, history size
-    int nblk;                     // CTAs per frame in the two streaming passes
+    int nblk;                     // CTAs per frame in the update pass
+    int nblk_dots;                // CTAs per frame in the dot-product pass
     float* x;                     // [NB][n] (caller's image, fp32 NCHW)
     const float* g;               // [NB][n] gradient of the last closure
     const float* losses;          // [NB][loss_stride], total at index loss_total
@@ -103,16 +104,35 @@ __device__ __forceinline__ void lb_store16(float* __restrict__ p, size_t base, i
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// pass 1: all dot products of this iteration. grid (nblk, NB), 256 threads; each warp owns whole warp-tiles, so there
+// pass 1: all dot products of this iteration. grid (nblk_dots, NB), 12 warps; each warp owns whole warp-tiles, so there
 // is no block-level synchronisation inside the history loop.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// The history tiles (2 KB of S_i and 2 KB of Y_i per warp and pair) arrive through a per-warp shared-memory ring filled by 1-D
+// bulk copies (cp.async.bulk + mbarrier): LB_DOTS_DEPTH pairs = 12 KB per warp are in flight whatever the register budget,
+// ~18 MB over the GPU, which is what HBM needs at its latency (register-staged loads kept 4 KB per warp in flight and ran at
+// 4.7 TB/s). One CTA per SM, 12 warps, every warp owns whole warp-tiles.
+constexpr int LB_DOTS_WARPS = 12, LB_DOTS_DEPTH = 3;
+constexpr int LB_DOTS_RING = LB_DOTS_WARPS * LB_DOTS_DEPTH * 2 * LB_WT * 4;                 // 147456
+constexpr int LB_DOTS_BARS = 512;                                                             // 36 mbarriers
+constexpr int LB_DOTS_SMEM = LB_DOTS_RING + LB_DOTS_BARS + LB_DOTS_WARPS * LB_PART * 8 + 1024;  // + per-warp fp64 sums
+__global__ void __launch_bounds__(LB_DOTS_WARPS * 32, 1)
 lbfgs_dots_kernel(const LbParams P) {
-    __shared__ double wacc[8][LB_PART];
+    extern __shared__ uint8_t lb_ring_raw[];
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const LbFrame& F = P.frames[b];
+    // dynamic shared memory: [ring of every warp][mbarriers][per-warp fp64 accumulators]
+    const uint32_t ring_base = (smem_u32(lb_ring_raw) + 1023u) & ~1023u;
+    double (*wacc)[LB_PART] = reinterpret_cast<double (*)[LB_PART]>(lb_ring_raw + (ring_base - smem_u32(lb_ring_raw)) + LB_DOTS_RING + LB_DOTS_BARS);
     for (int i = lane; i < LB_PART; i += 32) wacc[warp][i] = 0.0;
     wacc[warp][5 * LB_MAXH + 6] = 0.0;
+    // ring of this warp: LB_DOTS_DEPTH stages of [S tile 2 KB][Y tile 2 KB], one mbarrier per stage
+    const uint32_t my_ring = ring_base + (uint32_t)warp * LB_DOTS_DEPTH * 2 * LB_WT * 4;
+    const uint32_t my_bars = ring_base + LB_DOTS_RING + (uint32_t)warp * LB_DOTS_DEPTH * 8;
+    const float* ring_f = reinterpret_cast<const float*>(lb_ring_raw + (my_ring - smem_u32(lb_ring_raw)));
+    if (lane == 0) {
+        for (int s = 0; s < LB_DOTS_DEPTH; ++s) mbar_init(my_bars + 8u * s, 1);
+        fence_barrier_init();
+    }
     __syncwarp();
     pdl_trigger();
     pdl_wait();          // the frame state, the gradient and the history are written by the previous kernels of the stream
@@ -125,10 +145,23 @@ lbfgs_dots_kernel(const LbParams P) {
     const int hist = F.hist_len, head = F.head, m = P.m;
     const int ntiles = (n + LB_WT - 1) / LB_WT;
     float gmax = 0.f;
+    uint32_t used = 0;                   // stage uses of this warp so far (ring position = used % DEPTH, parity = used / DEPTH)
     if (!skip) {
-        for (int tile = blockIdx.x * 8 + warp; tile < ntiles; tile += gridDim.x * 8) {
+        for (int tile = blockIdx.x * LB_DOTS_WARPS + warp; tile < ntiles; tile += gridDim.x * LB_DOTS_WARPS) {
             const size_t base = (size_t)tile * LB_WT;
             const int n_left = n - (int)base;
+            const uint32_t tile_bytes = (uint32_t)((n_left < LB_WT ? n_left : LB_WT) * 4);
+            auto slot_of = [&](int i) { int s = head + i; return s >= m ? s - m : s; };
+            auto issue = [&](int i, uint32_t use) {          // lane 0: fetch pair i into ring stage use % DEPTH
+                const uint32_t st = use % LB_DOTS_DEPTH;
+                const size_t ho = ((size_t)slot_of(i) * P.NB + b) * (size_t)n + base;
+                const uint32_t dst = my_ring + st * (2 * LB_WT * 4), bar = my_bars + 8u * st;
+                mbar_arrive_expect_tx(bar, 2 * tile_bytes);
+                bulk_load_1d(dst, P.S + ho, tile_bytes, bar);
+                bulk_load_1d(dst + LB_WT * 4, P.Y + ho, tile_bytes, bar);
+            };
+            if (vec && lane == 0)
+                for (int i = 0; i < LB_DOTS_DEPTH && i < hist; ++i) issue(i, used + (uint32_t)i);
             float gv[16], yv[16], sv[16];
             lb_load16(P.g + fo, base, n_left, lane, vec, gv);
             if (has_prev) {
@@ -153,12 +186,31 @@ lbfgs_dots_kernel(const LbParams P) {
                 st[0] += a0; st[1] += a1; st[2] += a2; st[3] += a3; st[4] += a4; st[5] += a5;
             }
             for (int i = 0; i < hist; ++i) {
-                int slot = head + i;
-                if (slot >= m) slot -= m;
-                const size_t ho = ((size_t)slot * P.NB + b) * (size_t)n;
+                const int slot = slot_of(i);
                 float s_i[16], y_i[16];
-                lb_load16(P.S + ho, base, n_left, lane, vec, s_i);
-                lb_load16(P.Y + ho, base, n_left, lane, vec, y_i);
+                if (vec) {
+                    const uint32_t use = used + (uint32_t)i, st = use % LB_DOTS_DEPTH;
+                    mbar_wait(my_bars + 8u * st, (use / LB_DOTS_DEPTH) & 1u);
+                    const float* sp = ring_f + st * (2 * LB_WT);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int off = k * 128 + lane * 4;
+                        const bool in = off + 3 < n_left;          // n % 4 == 0: a float4 is inside or outside as a whole
+                        const float4 a = in ? *reinterpret_cast<const float4*>(sp + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 c = in ? *reinterpret_cast<const float4*>(sp + LB_WT + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        s_i[4 * k] = a.x; s_i[4 * k + 1] = a.y; s_i[4 * k + 2] = a.z; s_i[4 * k + 3] = a.w;
+                        y_i[4 * k] = c.x; y_i[4 * k + 1] = c.y; y_i[4 * k + 2] = c.z; y_i[4 * k + 3] = c.w;
+                    }
+                    __syncwarp();                                    // every lane has read the stage
+                    if (lane == 0 && i + LB_DOTS_DEPTH < hist) {
+                        fence_proxy_async_smem();                    // generic reads before the async-proxy refill
+                        issue(i + LB_DOTS_DEPTH, use + LB_DOTS_DEPTH);
+                    }
+                } else {
+                    const size_t ho = ((size_t)slot * P.NB + b) * (size_t)n;
+                    lb_load16(P.S + ho, base, n_left, lane, vec, s_i);
+                    lb_load16(P.Y + ho, base, n_left, lane, vec, y_i);
+                }
                 float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
@@ -174,18 +226,19 @@ lbfgs_dots_kernel(const LbParams P) {
                     a[0] += c0; a[1] += c1; a[2] += c2; a[3] += c3; a[4] += c4;
                 }
             }
+            if (vec) used += (uint32_t)hist;
         }
         gmax = warp_max(gmax);
         if (lane == 0) wacc[warp][5 * LB_MAXH + 6] = gmax;
     }
     __syncthreads();
-    double* out = P.part + ((size_t)b * P.nblk + blockIdx.x) * LB_PART;
+    double* out = P.part + ((size_t)b * P.nblk_dots + blockIdx.x) * LB_PART;
     for (int i = threadIdx.x; i < LB_PART; i += blockDim.x) {
         double s = 0.0;
         if (i == 5 * LB_MAXH + 6) {
-            for (int w = 0; w < 8; ++w) s = fmax(s, wacc[w][i]);
+            for (int w = 0; w < LB_DOTS_WARPS; ++w) s = fmax(s, wacc[w][i]);
         } else {
-            for (int w = 0; w < 8; ++w) s += wacc[w][i];
+            for (int w = 0; w < LB_DOTS_WARPS; ++w) s += wacc[w][i];
         }
         out[i] = s;
     }
@@ -209,10 +262,10 @@ lbfgs_reduce_kernel(const LbParams P) {
         F.t_prev_f = (float)F.t;
     }
     if (i >= LB_PART) return;
-    const double* p = P.part + (size_t)b * P.nblk * LB_PART + i;
+    const double* p = P.part + (size_t)b * P.nblk_dots * LB_PART + i;
     const bool is_max = (i == 5 * LB_MAXH + 6);
     double s = 0.0;
-    for (int k = lane; k < P.nblk; k += 32) {
+    for (int k = lane; k < P.nblk_dots; k += 32) {
         const double v = p[(size_t)k * LB_PART];
         s = is_max ? fmax(s, v) : s + v;
     }
@@ -506,8 +559,8 @@ inline int lbfgs_enqueue_step(ist_lbfgs* O, float* x, cudaStream_t st) {
         IST_TRY(rc_closure);
         P.it = it;
         const double vb = 4.0 * P.NB * (double)P.n;
-        IST_EWK("lbfgs_dots", vb * (3 + 2.0 * P.m), st, PDL_OPT, lbfgs_dots_kernel, dim3(P.nblk, P.NB), 256, 0, P);
-        IST_EWK("lbfgs_reduce", 8.0 * P.NB * P.nblk * LB_PART, st, PDL_OPT, lbfgs_reduce_kernel, dim3((LB_PART + 7) / 8, P.NB), 256, 0, P);
+        IST_EWK("lbfgs_dots", vb * (3 + 2.0 * P.m), st, PDL_OPT, lbfgs_dots_kernel, dim3(P.nblk_dots, P.NB), LB_DOTS_WARPS * 32, LB_DOTS_SMEM, P);
+        IST_EWK("lbfgs_reduce", 8.0 * P.NB * P.nblk_dots * LB_PART, st, PDL_OPT, lbfgs_reduce_kernel, dim3((LB_PART + 7) / 8, P.NB), 256, 0, P);
         IST_EWK("lbfgs_solve", 16.0 * P.m * P.m, st, PDL_OPT, lbfgs_solve_kernel, P.NB, LB_SOLVE_THREADS, lb_solve_smem(P.m), P);
         IST_EWK("lbfgs_update", vb * (9 + 2.0 * P.m), st, PDL_OPT, lbfgs_update_kernel, dim3(P.nblk, P.NB), 256, 0, P);
     }
@@ -537,6 +590,10 @@ int ist_lbfgs_create(ist_lbfgs** out, ist_plan* plan, int history_size, int max_
     if (nblk > 2 * num_sms()) nblk = 2 * num_sms();
     if (nblk < 1) nblk = 1;
     P.nblk = nblk;
+    int nblk_dots = (ntiles + LB_DOTS_WARPS - 1) / LB_DOTS_WARPS;        // one CTA per SM (its ring takes the shared memory)
+    if (nblk_dots > num_sms()) nblk_dots = num_sms();
+    if (nblk_dots < 1) nblk_dots = 1;
+    P.nblk_dots = nblk_dots;
     P.max_iter = max_iter;
     P.max_eval = max_eval > 0 ? max_eval : max_iter * 5 / 4;
     P.lr = lr; P.tol_grad = tolerance_grad; P.tol_change = tolerance_change;
@@ -552,7 +609,7 @@ int ist_lbfgs_create(ist_lbfgs** out, ist_plan* plan, int history_size, int max_
     if (rc == IST_OK) rc = O->mem.alloc(&P.d, vn);
     if (rc == IST_OK) rc = O->mem.alloc(&P.S, vn * P.m);
     if (rc == IST_OK) rc = O->mem.alloc(&P.Y, vn * P.m);
-    if (rc == IST_OK) rc = O->mem.alloc(&P.part, (size_t)P.NB * P.nblk * LB_PART);
+    if (rc == IST_OK) rc = O->mem.alloc(&P.part, (size_t)P.NB * P.nblk_dots * LB_PART);
     if (rc == IST_OK) rc = O->mem.alloc(&P.tot, (size_t)P.NB * LB_PART);
     if (rc == IST_OK) rc = O->mem.alloc(&P.dmax_part, (size_t)P.NB * P.nblk);
     if (rc == IST_OK) rc = O->mem.alloc(&P.SY, (size_t)P.NB * LB_MAXH * LB_MAXH);
@@ -569,6 +626,7 @@ int ist_lbfgs_create(ist_lbfgs** out, ist_plan* plan, int history_size, int max_
     cudaMemset(P.prev_g, 0, sizeof(float) * vn);
     cudaError_t e = cudaFuncSetAttribute(lbfgs_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)lb_solve_smem(history_size));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lbfgs_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_DOTS_SMEM);
     if (e != cudaSuccess) { delete O; return fail(IST_ERR_CUDA, "cudaFuncSetAttribute(lbfgs_solve): %s", cudaGetErrorString(e)); }
     const char* ng = getenv("IST_B200_NO_GRAPH");
     O->use_graph = !(ng != nullptr && atoi(ng) == 1);
