@@ -4,8 +4,10 @@
 // result is x.grad of IST/model/engine/utils.py:36). As an implicit GEMM: M = pixels (tiles of 16 x 8), K = 64 channels x 9
 // taps, N = 3 padded to 16. The CUDA-core kernel (conv_first_dgrad_kernel) is shared-memory / L1 bound at ~1 TB/s (72 us at
 // 512^2 for 70 MB); here the dY halo tile of conv_halo.cuh feeds all nine taps of an M = 128, N = 16 tcgen05.mma, whose cost is
-// the 4 KB of A it reads per instruction. bf16 hi/lo split operands, three MMAs per product like every other data-gradient:
-// hi*hi in one accumulator (one chain of 36 MMAs per tile), the two cross terms in a second one.
+// the 4 KB of A it reads per instruction. bf16 hi/lo split operands and the three products of every other data-gradient, in
+// TWO instructions per k-slice: the hi and lo weight planes of a tap are adjacent in shared memory (32 rows), so
+// dY_hi x [W_hi ; W_lo] is one N = 32 MMA (columns 0-15 = hi*hi, 16-31 = hi*lo) and dY_lo x W_hi one N = 16 MMA — the A
+// operand is read twice instead of three times.
 // Warp roles (224 threads, persistent): warp 0 TMA producer (weights once: 9 taps x 2 planes x 2 KB; dY ring of 3 halo tiles),
 // warps 1 and 6 MMA issuers (taps 0-4 and 5-8, each with its own pair of accumulators: a single issuing thread sustains one
 // small SS-mode MMA per ~50 cycles and was the bound at 45 us), warps 2-5 read the accumulators (double-buffered over tiles),
@@ -19,6 +21,7 @@ struct CfdTcParams {
     int NB, H, W, tiles_x, tiles_y;
     float* grad;            // fp32 NCHW [NB, 3, H, W]
     uint32_t idesc;         // M = 128, N = 16, bf16 x bf16, both K-major
+    uint32_t idesc32;       // same with N = 32 (hi and lo weight planes in one instruction)
 };
 
 struct CfdTcCfg {
@@ -30,7 +33,7 @@ struct CfdTcCfg {
     static constexpr int N_PAD = 16;
     static constexpr int B_TAP = N_PAD * 128;                      // one tap, one plane: 16 rows of 64 channels
     static constexpr int B_BYTES = 9 * 2 * B_TAP;                  // 36864
-    static constexpr int TMEM_COLS = 128;                          // 2 tiles x 2 issuers x (main 16 + cross 16)
+    static constexpr int TMEM_COLS = 256;                          // 2 tiles x 2 issuers x (hi*[hi;lo] 32 + lo*hi 16, padded to 64)
     static constexpr int SMEM_BYTES = A_STAGES * A_STAGE + B_BYTES + 256 + 1024;
 };
 
@@ -107,7 +110,7 @@ conv_first_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __g
         const int tap_begin = issuer == 0 ? 0 : 5, tap_end = issuer == 0 ? 5 : 9;
         const uint32_t a_hi_w = (((uint32_t)(Cfg::PW * 128) >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
         const uint32_t b_hi_w = (1024u >> 4) | (1u << 14) | (2u << 29);
-        const uint32_t idesc = p.idesc;
+        const uint32_t idesc = p.idesc, idesc32 = p.idesc32;
         int as = 0;
         uint32_t aph = 0, cnt = 0;
         mbar_wait(bfull, 0);
@@ -117,7 +120,7 @@ conv_first_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __g
             mbar_wait(afull(as), aph);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t d_main = tmem_base + ab * 64u + (uint32_t)issuer * 32u, d_cross = d_main + 16u;
+                const uint32_t d_main = tmem_base + ab * 128u + (uint32_t)issuer * 64u, d_cross = d_main + 32u;
                 const uint32_t a_stage = (a_base + as * Cfg::A_STAGE) >> 4;
                 for (int tap = tap_begin; tap < tap_end; ++tap) {
                     const uint32_t a_lo = a_stage + (uint32_t)(((tap / 3) * Cfg::PW + (tap % 3)) * 8);
@@ -125,9 +128,8 @@ conv_first_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __g
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
                         const uint32_t acc = ((tap - tap_begin) | k4) != 0 ? 1u : 0u;
-                        umma_f16_lh(d_main, a_lo + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, acc);
-                        umma_f16_lh(d_cross, a_lo + 2 * k4, a_hi_w, b_lo + (Cfg::B_TAP >> 4) + 2 * k4, b_hi_w, idesc, acc);
-                        umma_f16_lh(d_cross, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, 1u);
+                        umma_f16_lh(d_main, a_lo + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc32, acc);             // hi * [hi ; lo]
+                        umma_f16_lh(d_cross, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, acc);   // lo * hi
                     }
                 }
                 umma_commit(aempty(as));
@@ -147,11 +149,14 @@ conv_first_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __g
             const uint32_t ab = cnt & 1u;
             mbar_wait(accfull(ab), (cnt >> 1) & 1u);
             tc_fence_after();
-            uint32_t rm[16], rc[16], rm2[16], rc2[16];
-            tmem_ld_32x16(lane_base + ab * 64u, rm);
-            tmem_ld_32x16(lane_base + ab * 64u + 16u, rc);
-            tmem_ld_32x16(lane_base + ab * 64u + 32u, rm2);
-            tmem_ld_32x16(lane_base + ab * 64u + 48u, rc2);
+            // per issuer: columns [0,16) hi*hi, [16,32) hi*lo, [32,48) lo*hi; only the first three of each 16 are real channels
+            uint32_t rm[16], rc[16], rx[16], rm2[16], rc2[16], rx2[16];
+            tmem_ld_32x16(lane_base + ab * 128u, rm);
+            tmem_ld_32x16(lane_base + ab * 128u + 16u, rc);
+            tmem_ld_32x16(lane_base + ab * 128u + 32u, rx);
+            tmem_ld_32x16(lane_base + ab * 128u + 64u, rm2);
+            tmem_ld_32x16(lane_base + ab * 128u + 80u, rc2);
+            tmem_ld_32x16(lane_base + ab * 128u + 96u, rx2);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
@@ -160,8 +165,9 @@ conv_first_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __g
             if (gx < p.W && gy < p.H) {
                 float* dst = p.grad + (size_t)fr * 3 * HW + (size_t)gy * p.W + gx;
 #pragma unroll
-                for (int ci = 0; ci < 3; ++ci)          // fixed order: (main + main') + (cross + cross')
-                    dst[ci * HW] = (__uint_as_float(rm[ci]) + __uint_as_float(rm2[ci])) + (__uint_as_float(rc[ci]) + __uint_as_float(rc2[ci]));
+                for (int ci = 0; ci < 3; ++ci)          // fixed order: (main + main') + ((hi*lo + lo*hi) + (hi*lo + lo*hi)')
+                    dst[ci * HW] = (__uint_as_float(rm[ci]) + __uint_as_float(rm2[ci])) +
+                                   ((__uint_as_float(rc[ci]) + __uint_as_float(rx[ci])) + (__uint_as_float(rc2[ci]) + __uint_as_float(rx2[ci])));
             }
         }
     }

@@ -523,6 +523,7 @@ inline int launch_conv_first_dgrad_tc(cudaStream_t st, const CUtensorMap& a_hi, 
     p.tiles_y = (H + CfdTcCfg::TH - 1) / CfdTcCfg::TH;
     p.grad = grad;
     p.idesc = umma_idesc_f16(UMMA_FMT_BF16, 128, CfdTcCfg::N_PAD, 0, 0);
+    p.idesc32 = umma_idesc_f16(UMMA_FMT_BF16, 128, 2 * CfdTcCfg::N_PAD, 0, 0);
     const long long total = (long long)NB * p.tiles_x * p.tiles_y;
     const int grid = total < num_sms() ? (int)total : num_sms();
     const double px = (double)NB * H * W;
