@@ -36,7 +36,8 @@ struct CffTcCfg {
     static constexpr int W_SCALE_LOG2 = 8;                         // weights enter the MMA as fp16(256 * w)
     static constexpr int TMEM_COLS = 256;                          // 2 tiles x (main 64 + cross 64)
     static constexpr int THREADS = 13 * 32;                        // issuer, 4 builder warps, 8 epilogue warps
-    static constexpr int SMEM_BYTES = A_STAGES * A_STAGE + 2 * B_PLANE + 2 * OUT_PLANE + SX_BYTES + 256 + 1024;
+    static constexpr int OUT_BUFS = 2;                             // staging tiles in rotation: a tile is converted while the previous one's TMA store drains
+    static constexpr int SMEM_BYTES = A_STAGES * A_STAGE + 2 * B_PLANE + OUT_BUFS * 2 * OUT_PLANE + SX_BYTES + 256 + 1024;
 };
 
 __global__ void __launch_bounds__(CffTcCfg::THREADS, 1)
@@ -49,7 +50,7 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmO_hi, const __gri
     const uint32_t a_base = smem_base;
     const uint32_t b_base = a_base + Cfg::A_STAGES * Cfg::A_STAGE;
     const uint32_t o_base = b_base + 2 * Cfg::B_PLANE;
-    const uint32_t sx_base = o_base + 2 * Cfg::OUT_PLANE;
+    const uint32_t sx_base = o_base + Cfg::OUT_BUFS * 2 * Cfg::OUT_PLANE;
     const uint32_t bar_base = sx_base + Cfg::SX_BYTES;
     float* sx = reinterpret_cast<float*>(smem_al + (sx_base - smem_base));
     auto afull = [&](int s) { return bar_base + 8u * s; };
@@ -219,20 +220,21 @@ conv_first_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmO_hi, const __gri
             for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(rm[j]) + __uint_as_float(rc[j])) * alpha;
             uint32_t hi[16], lo[16];
             conv_epilogue_regs_32(cp, v, grp * 32, hi, lo);
-            if (storer) tma_store_wait_read();                       // the previous tile has left the staging buffer
+            const uint32_t o_buf = o_base + (cnt & 1u) * (2u * Cfg::OUT_PLANE);
+            if (storer) tma_store_wait_read_1();                     // the tile staged two tiles ago has left this buffer
             named_bar_sync(2, 256);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const uint32_t chunk = (uint32_t)((grp * 4 + q) ^ (m & 7));
-                const uint32_t a = o_base + (uint32_t)m * 128u + chunk * 16u;
+                const uint32_t a = o_buf + (uint32_t)m * 128u + chunk * 16u;
                 st_shared_v4(a, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
                 st_shared_v4(a + Cfg::OUT_PLANE, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
             }
             fence_proxy_async_smem();
             named_bar_sync(2, 256);
             if (storer) {
-                tma_store_4d(&tmO_hi, o_base, 0, tx * Cfg::TW, ty * Cfg::TH, fr);
-                tma_store_4d(&tmO_lo, o_base + Cfg::OUT_PLANE, 0, tx * Cfg::TW, ty * Cfg::TH, fr);
+                tma_store_4d(&tmO_hi, o_buf, 0, tx * Cfg::TW, ty * Cfg::TH, fr);
+                tma_store_4d(&tmO_lo, o_buf + Cfg::OUT_PLANE, 0, tx * Cfg::TW, ty * Cfg::TH, fr);
                 tma_store_commit();
             }
         }
