@@ -113,3 +113,27 @@ def test_closure_is_bitwise_deterministic_and_batch_consistent(model_cfg, size):
     assert torch.equal(lb[0], l_a[0]) and torch.equal(gb[0], g_a[0])
     assert torch.equal(lb[1], l_c[0]) and torch.equal(gb[1], g_c[0])
     assert torch.equal(lb[2], l_a[0]) and torch.equal(gb[2], g_a[0])
+
+
+@pytest.mark.parametrize("h,w", [(70, 52), (37, 90)])
+def test_closure_odd_sizes(model_cfg, h, w):
+    """Image sizes that are no multiple of the 16 x 8 pixel tile (Scale keeps the aspect ratio, so e.g. 512 x 683 frames occur):
+    partial and phantom tiles of the CTA-pair conv kernel and of the tensor-core first-conv kernels, odd pool edges."""
+    cfg, model = model_cfg
+    content, style = frames(max(h, w), dev, "smooth", h=h, w=w)
+    plan = prepare_plan(model, cfg, content, style)
+    state_np = synth.vgg_state_dict(0, upto="conv5_1")
+    st64 = O.state_to_torch(state_np, torch.float64, dev)
+    st32 = O.state_to_torch(state_np, torch.float32, dev)
+    t64 = O.compute_targets(st64, content.double(), style.double(), full=False)
+    t32 = O.compute_targets(st32, content, style, full=False)
+    x = content + noise_like(content)
+    losses, grad = plan.loss_and_grad(x)
+    l64, tot64, g64 = O.loss_and_grad(st64, x.double(), t64, full=False)
+    _, _, g32 = O.loss_and_grad(st32, x, t32, full=False)
+    ours = losses[0].double().cpu().numpy()
+    ref = np.array(l64 + [tot64])
+    assert np.all(np.abs(ours - ref) / np.abs(ref) < 1e-4), (ours, ref)
+    err, floor = rel_l2(grad, g64), rel_l2(g32, g64)
+    print(f"{h}x{w}: grad rel-L2 ours {err:.2e}, oracle fp32-vs-fp64 {floor:.2e}")
+    assert err <= max(2e-3, 3 * floor)
