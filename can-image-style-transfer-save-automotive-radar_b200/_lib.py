@@ -67,6 +67,7 @@ SIGNATURES = {
     "ist_version": (ctypes.c_int, []),
     "ist_device_check": (ctypes.c_int, []),
     "ist_launch_count": (ctypes.c_ulonglong, []),
+    "ist_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "ist_profile_begin": (ctypes.c_int, []),
     "ist_profile_end": (ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), _c_float_p, _c_int_p]),
     "ist_plan_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.POINTER(LayerDesc), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
@@ -76,6 +77,7 @@ SIGNATURES = {
     "ist_plan_forward": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
     "ist_plan_get_feature": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
     "ist_plan_feature_shape": (ctypes.c_int, [_vp, ctypes.c_int, _c_int_p, _c_int_p, _c_int_p]),
+    "ist_plan_get_pool_index": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
     "ist_plan_gram": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
     "ist_plan_set_loss": (ctypes.c_int, [_vp, ctypes.c_int, _c_int_p, _c_float_p, ctypes.c_int, _c_int_p, _c_float_p]),
     "ist_plan_set_style_target": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
@@ -87,6 +89,10 @@ SIGNATURES = {
     "ist_lbfgs_reset": (ctypes.c_int, [_vp, _vp]),
     "ist_lbfgs_step": (ctypes.c_int, [_vp, _vp, _c_int_p, _c_float_p, _vp]),
     "ist_lbfgs_last_losses": (ctypes.c_int, [_vp, _c_float_p]),
+    "ist_lbfgs_frame_state": (ctypes.c_int, [_vp, ctypes.c_int, _c_int_p, _c_int_p, _c_int_p, _c_int_p, _c_int_p]),
+    "ist_lbfgs_set_trace": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int]),
+    "ist_lbfgs_trace_count": (ctypes.c_int, [_vp, _c_int_p]),
+    "ist_lbfgs_create_test": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_double]),
     "ist_image_resize_target": (ctypes.c_int, [ctypes.c_int] * 3 + [_c_int_p, _c_int_p]),
     "ist_image_post_u8": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 3 + [_c_double_p, _vp]),
     "ist_image_prep_u8": (ctypes.c_int, [_vp, _vp] + [ctypes.c_int] * 3 + [_c_double_p, _vp]),
@@ -140,11 +146,12 @@ def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def ptr(t):
-    """Device pointer of a contiguous fp32 CUDA tensor."""
+def ptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor of `dtype` (float32 unless stated)."""
     import torch
+    dtype = torch.float32 if dtype is None else dtype
     if not t.is_cuda:
         raise IstError("expected a CUDA tensor (the B200 path has no CPU fallback)")
-    if t.dtype != torch.float32 or not t.is_contiguous():
-        raise IstError("expected a contiguous float32 tensor")
+    if t.dtype != dtype or not t.is_contiguous():
+        raise IstError(f"expected a contiguous {dtype} tensor")
     return ctypes.c_void_p(t.data_ptr())

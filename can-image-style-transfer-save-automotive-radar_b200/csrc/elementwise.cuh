@@ -93,6 +93,17 @@ __global__ void planes_to_nchw_kernel(const uint16_t* __restrict__ hi, const uin
         dst[((size_t)n * C + 2 * cp + 1) * HW + pix] = b * inv_scale;
     }
 }
+// argmax bytes of a pool layer, NHWC [NB,HW,C] -> NCHW [NB,C,HW] (ist_plan_get_pool_index)
+__global__ void u8_nhwc_to_nchw_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int NB, int C, int HW) {
+    const size_t total = (size_t)NB * HW * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int pix = (int)(i % HW);
+        const size_t nc = i / HW;
+        const int c = (int)(nc % C);
+        const int n = (int)(nc / C);
+        dst[i] = src[((size_t)n * HW + pix) * C + c];
+    }
+}
 __global__ void nchw_to_nhwc_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int NB, int C, int HW) {
     const size_t total = (size_t)NB * HW * C;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {

@@ -129,15 +129,47 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     return launch_kc(kernel, grid, block, smem, st, pdl, 1, std::forward<Args>(args)...);
 }
 
-inline int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+// Per-device caches: function attributes (cudaFuncSetAttribute) and device properties belong to the CURRENT device, and a
+// process may drive several (MODEL.DEVICE = 'cuda:1' while device 0 is current elsewhere; one process per GPU is the normal
+// multi-GPU mode, but the reference lets the user pick any device through torch).
+constexpr int IST_MAX_DEVICES = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < IST_MAX_DEVICES) ? dev : 0;
+}
+// Makes `dev` current for the duration of a C-ABI call on an object bound to that device (plans and optimisers remember the
+// device they were created on), and restores the caller's device afterwards.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (dev >= 0 && dev != prev) switched = (cudaSetDevice(dev) == cudaSuccess);
     }
-    return n;
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+struct DeviceOnce {
+    bool done[IST_MAX_DEVICES] = {};
+    bool first() {                       // true exactly once per device
+        const int d = current_device();
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+inline int num_sms() {
+    static int n[IST_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
+    }
+    return n[dev];
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -233,11 +265,10 @@ inline int map_gram(CUtensorMap* m, const uint16_t* base, int NB, int HW, int C)
 template <int N_TILE>
 inline int launch_conv_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                          const CUtensorMap& b_lo, const ConvParams& p) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
         IST_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       ConvCfg<N_TILE>::SMEM_BYTES));
-        attr_done = true;
     }
     const int total = p.NB * p.tiles_x * p.tiles_y * p.tiles_n;
     const int grid = total < num_sms() ? total : num_sms();
@@ -263,11 +294,10 @@ template <int N_TILE, bool PAIR>
 inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                          const CUtensorMap& b_lo, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const CUtensorMap& f_hi,
                          const CUtensorMap& f_lo, const CUtensorMap& d_hi, const CUtensorMap& d_lo, const ConvParams& p) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
         IST_CUDA(cudaFuncSetAttribute(conv_halo_kernel<N_TILE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       HaloCfg<N_TILE, PAIR>::SMEM_BYTES));
-        attr_done = true;
     }
     const int total = p.NB * p.tiles_x * p.tiles_y * p.tiles_n;
     int groups = conv_workers() / p.sk_cpf;            // frame groups that fit side by side
@@ -380,8 +410,8 @@ struct ConvWorkspace {
     }
 };
 inline ConvWorkspace& global_conv_workspace() {
-    static ConvWorkspace w;
-    return w;
+    static ConvWorkspace w[IST_MAX_DEVICES];      // one per device: the buffers live in the device they were allocated on
+    return w[current_device()];
 }
 
 // o_hi / o_lo: optional tensor maps (map_act(..., taps = 1)) of the output planes; with them the conv_halo forward epilogue
@@ -456,10 +486,9 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
 
 inline int launch_conv_first_dgrad(cudaStream_t st, const uint16_t* g_hi, const uint16_t* g_lo, const float* w, float* grad, int NB,
                                    int H, int W, bool pdl = false) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
         IST_CUDA(cudaFuncSetAttribute(conv_first_dgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFD_SMEM));
-        attr_done = true;
     }
     const double px = (double)NB * H * W;
     launch_pre("conv_first_dgrad", 2.0 * px * 64 * 27, px * (12.0 + 256.0), st);
@@ -470,8 +499,9 @@ inline int launch_conv_first_dgrad(cudaStream_t st, const uint16_t* g_hi, const 
 }
 
 // conv1_1 forward on the tensor cores (conv_first_fwd_tc.cuh). IST_B200_CFF=cuda selects the CUDA-core kernel.
+inline int& cff_flag() { static int v = -1; return v; }      // -1 = not decided yet (environment), ist_set_option overrides
 inline int cff_use_tc() {
-    static int v = -1;
+    int& v = cff_flag();
     if (v < 0) {
         const char* e = getenv("IST_B200_CFF");
         v = (e != nullptr && strcmp(e, "cuda") == 0) ? 0 : 1;
@@ -480,10 +510,9 @@ inline int cff_use_tc() {
 }
 inline int launch_conv_first_fwd_tc(cudaStream_t st, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const float* x, const float* w,
                                     const float* bias, int NB, int H, int W, float out_scale, int pdl) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
         IST_CUDA(cudaFuncSetAttribute(conv_first_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CffTcCfg::SMEM_BYTES));
-        attr_done = true;
     }
     CffTcParams p;
     memset(&p, 0, sizeof(p));
@@ -501,8 +530,9 @@ inline int launch_conv_first_fwd_tc(cudaStream_t st, const CUtensorMap& o_hi, co
     return IST_OK;
 }
 // conv1_1 data-gradient on the tensor cores (conv_first_tc.cuh). IST_B200_CFD=cuda selects the CUDA-core kernel.
+inline int& cfd_flag() { static int v = -1; return v; }
 inline int cfd_use_tc() {
-    static int v = -1;
+    int& v = cfd_flag();
     if (v < 0) {
         const char* e = getenv("IST_B200_CFD");
         v = (e != nullptr && strcmp(e, "cuda") == 0) ? 0 : 1;
@@ -511,10 +541,9 @@ inline int cfd_use_tc() {
 }
 inline int launch_conv_first_dgrad_tc(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                                       const CUtensorMap& b_lo, float* grad, int NB, int H, int W, bool pdl) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
         IST_CUDA(cudaFuncSetAttribute(conv_first_dgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CfdTcCfg::SMEM_BYTES));
-        attr_done = true;
     }
     CfdTcParams p;
     memset(&p, 0, sizeof(p));
@@ -550,10 +579,9 @@ inline void gram_split_plan(int NB, int HW, int C, int* splits, int* chunks_per_
 }
 inline int launch_gram(cudaStream_t st, const CUtensorMap& m_hi, const CUtensorMap& m_lo, int NB, int HW, int C,
                        int splits, int chunks_per_split, float* partial, int passes, bool pdl = false) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
         IST_CUDA(cudaFuncSetAttribute(gram_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg::SMEM_BYTES));
-        attr_done = true;
     }
     if (C % 64 != 0 || (C > 64 && C % 128 != 0)) return fail(IST_ERR_ARG, "gram needs C == 64 or C %% 128 == 0 (got %d)", C);
     GramParams p;

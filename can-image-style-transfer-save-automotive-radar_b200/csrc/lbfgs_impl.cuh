@@ -22,6 +22,7 @@
 
 namespace ist {
 int plan_batch(const ist_plan* P);
+int plan_device(const ist_plan* P);
 int plan_image_elems(const ist_plan* P);
 int plan_n_losses(const ist_plan* P);
 void plan_set_pdl_first(ist_plan* P, bool on);
@@ -530,10 +531,81 @@ lbfgs_update_kernel(const LbParams P) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Diagnostics (tests only; never part of a graph unless ist_lbfgs_set_trace was called before the first step).
+// Trace: one record per closure evaluation and frame — the evaluation point x, the gradient g the closure returned, the
+// direction d the iteration computed from it and the scalar state after the solve. The records let a test feed exactly
+// these gradients to a float64 restatement of torch/optim/lbfgs.py and compare every direction, step size, H_diag, the
+// accepted / rejected curvature pairs and the exits ("teacher forcing": no chaotic amplification of rounding).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int LB_TRACE_SCALARS = 16;
+struct LbTrace {
+    float *x = nullptr, *g = nullptr, *d = nullptr;      // [cap][NB][n]
+    double* sc = nullptr;                                // [cap][NB][LB_TRACE_SCALARS]
+    int* count = nullptr;                                // device counter of complete records
+    int cap = 0;
+};
+__global__ void lbfgs_trace_pre_kernel(const LbParams P, const LbTrace T) {
+    const int e = *T.count, b = blockIdx.y;
+    if (e >= T.cap) return;
+    const size_t src = (size_t)b * P.n, dst = ((size_t)e * P.NB + b) * (size_t)P.n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)P.n; i += (size_t)gridDim.x * blockDim.x) {
+        T.x[dst + i] = P.x[src + i];
+        T.g[dst + i] = P.g[src + i];
+    }
+}
+__global__ void lbfgs_trace_post_kernel(const LbParams P, const LbTrace T) {
+    const int e = *T.count, b = blockIdx.y;
+    if (e >= T.cap) return;
+    const size_t src = (size_t)b * P.n, dst = ((size_t)e * P.NB + b) * (size_t)P.n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)P.n; i += (size_t)gridDim.x * blockDim.x)
+        T.d[dst + i] = P.d[src + i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const LbFrame& F = P.frames[b];
+        const double* st = P.tot + (size_t)b * LB_PART + 5 * LB_MAXH;
+        double* o = T.sc + ((size_t)e * P.NB + b) * LB_TRACE_SCALARS;
+        o[0] = (double)P.losses[(size_t)b * P.loss_stride + P.loss_total];
+        o[1] = F.cg != 0.f ? 1.0 : 0.0;       // an iteration (direction) was computed from this evaluation
+        o[2] = F.active; o[3] = F.n_iter; o[4] = F.hist_len; o[5] = F.head; o[6] = F.accepted;
+        o[7] = F.H_diag; o[8] = F.t; o[9] = F.gtd; o[10] = st[0]; o[11] = st[1]; o[12] = F.apply;
+        o[13] = F.func_evals; o[14] = F.current_evals; o[15] = F.new_slot;
+    }
+}
+__global__ void lbfgs_trace_bump_kernel(const LbTrace T) {
+    if (*T.count < T.cap) *T.count += 1;
+}
+
+// Test objective (ist_lbfgs_create_test): per frame f(x) = sum_i 0.5 a_i (x_i - b_i)^2 + c_i cos(x_i), separable, with
+// negative curvature where c_i cos(x_i) > a_i (rejected curvature pairs) and a closed-form float64 oracle. One CTA per
+// frame, fixed-order reduction (run-to-run identical like every other reduction of this library).
+struct LbTestObjective {
+    const float *a = nullptr, *b = nullptr, *c = nullptr;      // [NB][n]
+};
+__global__ void __launch_bounds__(1024) lbfgs_test_objective_kernel(const LbTestObjective T, const float* __restrict__ x,
+                                                                     float* __restrict__ g, float* __restrict__ losses, int n) {
+    __shared__ double red[1024];
+    const int b = blockIdx.x;
+    const size_t fo = (size_t)b * n;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float xi = x[fo + i], r = xi - T.b[fo + i], ai = T.a[fo + i], ci = T.c[fo + i];
+        g[fo + i] = ai * r - ci * sinf(xi);
+        acc += 0.5 * (double)ai * (double)r * (double)r + (double)ci * (double)cosf(xi);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) losses[b] = (float)red[0];
+}
+
 }  // namespace ist
 
 struct ist_lbfgs {
     ist_plan* plan = nullptr;
+    int device = -1;
     ist::LbParams P;
     ist::DevMem mem;
     float* g = nullptr;
@@ -545,6 +617,8 @@ struct ist_lbfgs {
     bool use_graph = true;
     unsigned long long graph_kernels = 0;
     std::vector<ist::LbFrame> host_frames;
+    ist::LbTrace trace;                 // diagnostics (ist_lbfgs_set_trace)
+    ist::LbTestObjective test_obj;      // closure of ist_lbfgs_create_test (plan == nullptr)
 };
 
 namespace ist {
@@ -553,16 +627,28 @@ inline int lbfgs_enqueue_step(ist_lbfgs* O, float* x, cudaStream_t st) {
     LbParams P = O->P;
     P.x = x;
     for (int it = 1; it <= P.max_iter; ++it) {
-        plan_set_pdl_first(O->plan, it > 1);      // the closure then follows lbfgs_update_kernel on the same stream
-        const int rc_closure = ist_plan_loss_and_grad(O->plan, x, O->g, O->losses, (void*)st);
-        plan_set_pdl_first(O->plan, false);
-        IST_TRY(rc_closure);
+        if (O->plan != nullptr) {
+            plan_set_pdl_first(O->plan, it > 1 && O->trace.cap == 0);      // the closure then follows lbfgs_update_kernel on the same stream
+            const int rc_closure = ist_plan_loss_and_grad(O->plan, x, O->g, O->losses, (void*)st);
+            plan_set_pdl_first(O->plan, false);
+            IST_TRY(rc_closure);
+        } else {
+            IST_EW("lbfgs_test_objective", 16.0 * P.NB * P.n, st,
+                   lbfgs_test_objective_kernel<<<P.NB, 1024, 0, st>>>(O->test_obj, x, O->g, O->losses, P.n));
+        }
         P.it = it;
+        const int tgrid = (P.n + 1023) / 1024 < 64 ? (P.n + 1023) / 1024 : 64;
+        if (O->trace.cap > 0)
+            IST_EW("lbfgs_trace", 0.0, st, lbfgs_trace_pre_kernel<<<dim3(tgrid, P.NB), 256, 0, st>>>(P, O->trace));
         const double vb = 4.0 * P.NB * (double)P.n;
         IST_EWK("lbfgs_dots", vb * (3 + 2.0 * P.m), st, PDL_OPT, lbfgs_dots_kernel, dim3(P.nblk_dots, P.NB), LB_DOTS_WARPS * 32, LB_DOTS_SMEM, P);
         IST_EWK("lbfgs_reduce", 8.0 * P.NB * P.nblk_dots * LB_PART, st, PDL_OPT, lbfgs_reduce_kernel, dim3((LB_PART + 7) / 8, P.NB), 256, 0, P);
         IST_EWK("lbfgs_solve", 16.0 * P.m * P.m, st, PDL_OPT, lbfgs_solve_kernel, P.NB, LB_SOLVE_THREADS, lb_solve_smem(P.m), P);
         IST_EWK("lbfgs_update", vb * (9 + 2.0 * P.m), st, PDL_OPT, lbfgs_update_kernel, dim3(P.nblk, P.NB), 256, 0, P);
+        if (O->trace.cap > 0) {
+            IST_EW("lbfgs_trace", 0.0, st, lbfgs_trace_post_kernel<<<dim3(tgrid, P.NB), 256, 0, st>>>(P, O->trace));
+            IST_EW("lbfgs_trace", 0.0, st, lbfgs_trace_bump_kernel<<<1, 1, 0, st>>>(O->trace));
+        }
     }
     return IST_OK;
 }
@@ -571,19 +657,19 @@ inline int lbfgs_enqueue_step(ist_lbfgs* O, float* x, cudaStream_t st) {
 
 extern "C" {
 
-int ist_lbfgs_create(ist_lbfgs** out, ist_plan* plan, int history_size, int max_iter, int max_eval, float lr,
-                     double tolerance_grad, double tolerance_change) {
+static int lbfgs_create_common(ist_lbfgs** out, ist_plan* plan, int batch, int n, int n_losses, int history_size, int max_iter,
+                               int max_eval, float lr, double tolerance_grad, double tolerance_change) {
     using namespace ist;
-    if (out == nullptr || plan == nullptr) return fail(IST_ERR_ARG, "ist_lbfgs_create: null argument");
     if (history_size < 1 || history_size > LB_MAXH - 1) return fail(IST_ERR_ARG, "history_size must be in [1, %d]", LB_MAXH - 1);
     if (max_iter < 1) return fail(IST_ERR_ARG, "max_iter must be >= 1");
-    if (plan_n_losses(plan) < 1) return fail(IST_ERR_STATE, "configure the plan's losses before creating the optimiser");
+    DeviceGuard dg(plan != nullptr ? plan_device(plan) : -1);
     ist_lbfgs* O = new ist_lbfgs();
     O->plan = plan;
+    O->device = current_device();
     LbParams& P = O->P;
     memset(&P, 0, sizeof(P));
-    P.NB = plan_batch(plan);
-    P.n = plan_image_elems(plan);
+    P.NB = batch;
+    P.n = n;
     P.m = history_size;
     const int ntiles = (P.n + LB_WT - 1) / LB_WT;
     int nblk = (ntiles + 7) / 8;
@@ -597,7 +683,7 @@ int ist_lbfgs_create(ist_lbfgs** out, ist_plan* plan, int history_size, int max_
     P.max_iter = max_iter;
     P.max_eval = max_eval > 0 ? max_eval : max_iter * 5 / 4;
     P.lr = lr; P.tol_grad = tolerance_grad; P.tol_change = tolerance_change;
-    O->n_losses = plan_n_losses(plan);
+    O->n_losses = n_losses;
     P.loss_stride = O->n_losses + 1;
     P.loss_total = O->n_losses;
     const size_t vn = (size_t)P.NB * P.n;
@@ -615,6 +701,7 @@ int ist_lbfgs_create(ist_lbfgs** out, ist_plan* plan, int history_size, int max_
     if (rc == IST_OK) rc = O->mem.alloc(&P.SY, (size_t)P.NB * LB_MAXH * LB_MAXH);
     if (rc == IST_OK) rc = O->mem.alloc(&P.YY, (size_t)P.NB * LB_MAXH * LB_MAXH);
     if (rc == IST_OK) rc = O->mem.alloc(&P.frames, (size_t)P.NB);
+    if (rc == IST_OK) rc = O->mem.alloc(&O->trace.count, (size_t)1);
     if (rc != IST_OK) { delete O; return rc; }
     P.g = O->g;
     P.losses = O->losses;
@@ -624,6 +711,7 @@ int ist_lbfgs_create(ist_lbfgs** out, ist_plan* plan, int history_size, int max_
     cudaMemset(P.YY, 0, sizeof(double) * P.NB * LB_MAXH * LB_MAXH);
     cudaMemset(P.d, 0, sizeof(float) * vn);
     cudaMemset(P.prev_g, 0, sizeof(float) * vn);
+    cudaMemset(O->trace.count, 0, sizeof(int));
     cudaError_t e = cudaFuncSetAttribute(lbfgs_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)lb_solve_smem(history_size));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lbfgs_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_DOTS_SMEM);
@@ -635,8 +723,60 @@ int ist_lbfgs_create(ist_lbfgs** out, ist_plan* plan, int history_size, int max_
     return IST_OK;
 }
 
+int ist_lbfgs_create(ist_lbfgs** out, ist_plan* plan, int history_size, int max_iter, int max_eval, float lr,
+                     double tolerance_grad, double tolerance_change) {
+    using namespace ist;
+    if (out == nullptr || plan == nullptr) return fail(IST_ERR_ARG, "ist_lbfgs_create: null argument");
+    if (plan_n_losses(plan) < 1) return fail(IST_ERR_STATE, "configure the plan's losses before creating the optimiser");
+    return lbfgs_create_common(out, plan, plan_batch(plan), plan_image_elems(plan), plan_n_losses(plan), history_size, max_iter,
+                               max_eval, lr, tolerance_grad, tolerance_change);
+}
+
+int ist_lbfgs_create_test(ist_lbfgs** out, int batch, int n, const float* a_dev, const float* b_dev, const float* c_dev,
+                          int history_size, int max_iter, int max_eval, float lr, double tolerance_grad, double tolerance_change) {
+    using namespace ist;
+    if (out == nullptr || a_dev == nullptr || b_dev == nullptr || c_dev == nullptr || batch < 1 || n < 1)
+        return fail(IST_ERR_ARG, "ist_lbfgs_create_test: bad argument");
+    IST_TRY(ist_device_check());
+    IST_TRY(lbfgs_create_common(out, nullptr, batch, n, 0, history_size, max_iter, max_eval, lr, tolerance_grad, tolerance_change));
+    (*out)->test_obj.a = a_dev; (*out)->test_obj.b = b_dev; (*out)->test_obj.c = c_dev;
+    return IST_OK;
+}
+
+int ist_lbfgs_set_trace(ist_lbfgs* O, float* x_dev, float* g_dev, float* d_dev, double* scalars_dev, int capacity) {
+    using namespace ist;
+    if (O == nullptr || x_dev == nullptr || g_dev == nullptr || d_dev == nullptr || scalars_dev == nullptr || capacity < 1)
+        return fail(IST_ERR_ARG, "ist_lbfgs_set_trace: bad argument");
+    DeviceGuard dg(O->device);
+    if (O->graph_exec != nullptr) return fail(IST_ERR_STATE, "ist_lbfgs_set_trace must be called before the first step (the step graph is already captured)");
+    O->trace.x = x_dev; O->trace.g = g_dev; O->trace.d = d_dev; O->trace.sc = scalars_dev; O->trace.cap = capacity;
+    IST_CUDA(cudaMemset(O->trace.count, 0, sizeof(int)));
+    return IST_OK;
+}
+
+int ist_lbfgs_trace_count(ist_lbfgs* O, int* count_host) {
+    using namespace ist;
+    if (O == nullptr || count_host == nullptr) return fail(IST_ERR_ARG, "ist_lbfgs_trace_count: null argument");
+    DeviceGuard dg(O->device);
+    IST_CUDA(cudaMemcpy(count_host, O->trace.count, sizeof(int), cudaMemcpyDeviceToHost));
+    return IST_OK;
+}
+
+int ist_lbfgs_frame_state(ist_lbfgs* O, int frame, int* func_evals, int* n_iter, int* hist_len, int* active, int* step_evals) {
+    using namespace ist;
+    if (O == nullptr || frame < 0 || frame >= O->P.NB) return fail(IST_ERR_ARG, "ist_lbfgs_frame_state: bad argument");
+    const LbFrame& F = O->host_frames[frame];          // copied back by the last ist_lbfgs_step
+    if (func_evals != nullptr) *func_evals = F.func_evals;
+    if (n_iter != nullptr) *n_iter = F.n_iter;
+    if (hist_len != nullptr) *hist_len = F.hist_len;
+    if (active != nullptr) *active = F.active;
+    if (step_evals != nullptr) *step_evals = F.current_evals;
+    return IST_OK;
+}
+
 int ist_lbfgs_destroy(ist_lbfgs* O) {
     if (O == nullptr) return IST_OK;
+    ist::DeviceGuard dg(O->device);
     if (O->graph_exec != nullptr) cudaGraphExecDestroy(O->graph_exec);
     if (O->cap_stream != nullptr) cudaStreamDestroy(O->cap_stream);
     delete O;
@@ -646,17 +786,20 @@ int ist_lbfgs_destroy(ist_lbfgs* O) {
 int ist_lbfgs_reset(ist_lbfgs* O, void* stream) {
     using namespace ist;
     if (O == nullptr) return fail(IST_ERR_ARG, "ist_lbfgs_reset: null argument");
+    DeviceGuard dg(O->device);
     cudaStream_t st = (cudaStream_t)stream;
     const LbParams& P = O->P;
     // a fresh torch.optim.LBFGS([x]) (utils.py:24): empty state; the history buffers need no clearing (hist_len = 0)
     IST_CUDA(cudaMemsetAsync(P.frames, 0, sizeof(LbFrame) * P.NB, st));
     IST_CUDA(cudaMemsetAsync(P.dmax_part, 0, sizeof(float) * P.NB * P.nblk, st));
+    IST_CUDA(cudaMemsetAsync(O->trace.count, 0, sizeof(int), st));
     return IST_OK;
 }
 
 int ist_lbfgs_step(ist_lbfgs* O, float* x_dev, int* evals_out, float* loss_out, void* stream) {
     using namespace ist;
     if (O == nullptr || x_dev == nullptr) return fail(IST_ERR_ARG, "ist_lbfgs_step: null argument");
+    DeviceGuard dg(O->device);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t xbytes = sizeof(float) * (size_t)O->P.NB * O->P.n;
     if (O->use_graph) {
@@ -696,6 +839,7 @@ int ist_lbfgs_step(ist_lbfgs* O, float* x_dev, int* evals_out, float* loss_out, 
 int ist_lbfgs_last_losses(ist_lbfgs* O, float* losses_host) {
     using namespace ist;
     if (O == nullptr || losses_host == nullptr) return fail(IST_ERR_ARG, "ist_lbfgs_last_losses: null argument");
+    DeviceGuard dg(O->device);
     IST_CUDA(cudaMemcpy(losses_host, O->losses, sizeof(float) * O->P.NB * O->P.loss_stride, cudaMemcpyDeviceToHost));
     return IST_OK;
 }

@@ -57,8 +57,16 @@ int ist_op_conv3x3_relu_fwd(const float* x, const float* w, const float* b, floa
     IST_TRY(t.alloc(&ol, (size_t)NB * HW * cout));
     if (cin == 3) {
         if (cout != 64) return fail(IST_ERR_ARG, "first-layer kernel is built for cout == 64");
-        conv_first_fwd_kernel<64><<<dim3((W + CFF_TX - 1) / CFF_TX, (H + CFF_TY - 1) / CFF_TY, NB), 256, 0, st>>>(x, w, b, oh, ol, NB, H, W, kS);
-        IST_CUDA(cudaGetLastError());
+        // the dispatch of the plan (plan_impl.cuh run_forward): tensor-core kernel unless IST_B200_CFF=cuda
+        if (cff_use_tc() && conv_impl_halo()) {
+            CUtensorMap o_hi, o_lo;
+            IST_TRY(map_act(&o_hi, oh, NB, H, W, cout, 1));
+            IST_TRY(map_act(&o_lo, ol, NB, H, W, cout, 1));
+            IST_TRY(launch_conv_first_fwd_tc(st, o_hi, o_lo, x, w, b, NB, H, W, kS, 0));
+        } else {
+            conv_first_fwd_kernel<64><<<dim3((W + CFF_TX - 1) / CFF_TX, (H + CFF_TY - 1) / CFF_TY, NB), 256, 0, st>>>(x, w, b, oh, ol, NB, H, W, kS);
+            IST_CUDA(cudaGetLastError());
+        }
     } else {
         uint16_t *ih, *il, *fh, *fl, *dh, *dl;
         const size_t wn = (size_t)cout * cin * 9;
@@ -99,6 +107,20 @@ int ist_op_conv3x3_dgrad(const float* dy, const float* w, float* dx, int NB, int
     IST_TRY(to_planes(st, dy, gh, gl, NB, cout, HW, 1.f, true));
     if (cin == 3) {
         if (cout != 64) return fail(IST_ERR_ARG, "first-layer kernel is built for cout == 64");
+        // the dispatch of the plan (plan_impl.cuh run_backward): tensor-core kernel unless IST_B200_CFD=cuda
+        if (cfd_use_tc() && conv_impl_halo()) {
+            uint16_t *wh, *wl;
+            IST_TRY(t.alloc(&wh, (size_t)9 * CfdTcCfg::N_PAD * 64));
+            IST_TRY(t.alloc(&wl, (size_t)9 * CfdTcCfg::N_PAD * 64));
+            cfd_tc_weight_repack_kernel<<<36, 256, 0, st>>>(w, wh, wl);
+            IST_CUDA(cudaGetLastError());
+            CUtensorMap g_hi, g_lo, b_hi, b_lo;
+            IST_TRY(map_act(&g_hi, gh, NB, H, W, cout, 9));
+            IST_TRY(map_act(&g_lo, gl, NB, H, W, cout, 9));
+            IST_TRY(map_b(&b_hi, wh, 9, CfdTcCfg::N_PAD, 64, CfdTcCfg::N_PAD));
+            IST_TRY(map_b(&b_lo, wl, 9, CfdTcCfg::N_PAD, 64, CfdTcCfg::N_PAD));
+            return launch_conv_first_dgrad_tc(st, g_hi, g_lo, b_hi, b_lo, dx, NB, H, W, false);
+        }
         return launch_conv_first_dgrad(st, gh, gl, w, dx, NB, H, W);
     }
     uint16_t *fh, *fl, *dh, *dl;

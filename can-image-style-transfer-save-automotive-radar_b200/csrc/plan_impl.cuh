@@ -60,6 +60,7 @@ struct Layer {
 
 struct ist_plan {
     int NB = 0, H = 0, W = 0;
+    int device = -1;               // the CUDA device every buffer, tensor map and stream of this plan belongs to
     std::vector<Layer> layers;
     int n_conv = 0;
     DevMem mem;
@@ -398,6 +399,13 @@ const char* ist_last_error(void) { return last_error().c_str(); }
 int ist_version(void) { return 1; }
 int ist_device_check(void) { return check_device(); }
 
+int ist_set_option(const char* name, int value) {
+    if (name == nullptr) return fail(IST_ERR_ARG, "ist_set_option: null name");
+    if (strcmp(name, "first_conv_fwd_tc") == 0) { cff_flag() = value != 0 ? 1 : 0; return IST_OK; }
+    if (strcmp(name, "first_conv_dgrad_tc") == 0) { cfd_flag() = value != 0 ? 1 : 0; return IST_OK; }
+    return fail(IST_ERR_ARG, "ist_set_option: unknown option '%s'", name);
+}
+
 unsigned long long ist_launch_count(void) { return book().launches; }
 
 int ist_profile_begin(void) {
@@ -439,6 +447,7 @@ int ist_plan_create(ist_plan** out, int n_layers, const ist_layer_desc* layers, 
         return fail(IST_ERR_ARG, "first layer must be conv 3->64 (got kind %d %d->%d)", layers[0].kind, layers[0].cin, layers[0].cout);
     ist_plan* P = new ist_plan();
     P->NB = batch; P->H = H; P->W = W;
+    P->device = current_device();
     const char* pf = getenv("IST_B200_PASSES_FWD");
     const char* pb = getenv("IST_B200_PASSES_BWD");
     if (pf != nullptr && atoi(pf) == 1) P->passes_fwd = 1;
@@ -530,7 +539,10 @@ int ist_plan_create(ist_plan** out, int n_layers, const ist_layer_desc* layers, 
 }
 
 int ist_plan_destroy(ist_plan* plan) {
-    if (plan != nullptr) delete plan;
+    if (plan != nullptr) {
+        DeviceGuard dg(plan->device);
+        delete plan;
+    }
     return IST_OK;
 }
 
@@ -538,6 +550,7 @@ size_t ist_plan_bytes(const ist_plan* plan) { return plan != nullptr ? plan->mem
 
 int ist_plan_set_weights(ist_plan* P, int conv_index, const float* w_dev, const float* b_dev, void* stream) {
     if (P == nullptr || w_dev == nullptr || b_dev == nullptr) return fail(IST_ERR_ARG, "ist_plan_set_weights: null argument");
+    DeviceGuard dg(P->device);
     cudaStream_t st = (cudaStream_t)stream;
     for (Layer& L : P->layers) {
         if (L.kind != IST_LAYER_CONV3X3_RELU || L.conv_index != conv_index) continue;
@@ -574,6 +587,7 @@ int ist_plan_set_weights(ist_plan* P, int conv_index, const float* w_dev, const 
 
 int ist_plan_forward(ist_plan* P, const float* x_dev, int upto_layer, void* stream) {
     if (P == nullptr || x_dev == nullptr) return fail(IST_ERR_ARG, "ist_plan_forward: null argument");
+    DeviceGuard dg(P->device);
     if (upto_layer < 0 || upto_layer >= (int)P->layers.size()) return fail(IST_ERR_ARG, "ist_plan_forward: layer %d out of range", upto_layer);
     return run_forward(P, x_dev, upto_layer, (cudaStream_t)stream);
 }
@@ -589,6 +603,7 @@ int ist_plan_feature_shape(const ist_plan* P, int layer, int* C, int* h, int* w)
 
 int ist_plan_get_feature(ist_plan* P, int layer, float* out_dev, void* stream) {
     if (P == nullptr || out_dev == nullptr || layer < 0 || layer >= (int)P->layers.size()) return fail(IST_ERR_ARG, "ist_plan_get_feature: bad argument");
+    DeviceGuard dg(P->device);
     if (layer > P->forwarded_upto) return fail(IST_ERR_STATE, "layer %d has not been computed (forward ran to %d)", layer, P->forwarded_upto);
     const Layer& L = P->layers[layer];
     const size_t items = L.out_elems / 2;
@@ -598,8 +613,20 @@ int ist_plan_get_feature(ist_plan* P, int layer, float* out_dev, void* stream) {
     return IST_OK;
 }
 
+int ist_plan_get_pool_index(ist_plan* P, int layer, uint8_t* out_dev, void* stream) {
+    if (P == nullptr || out_dev == nullptr || layer < 0 || layer >= (int)P->layers.size()) return fail(IST_ERR_ARG, "ist_plan_get_pool_index: bad argument");
+    DeviceGuard dg(P->device);
+    const Layer& L = P->layers[layer];
+    if (L.kind != IST_LAYER_MAXPOOL2X2 || L.pool_idx == nullptr) return fail(IST_ERR_ARG, "layer %d is not a pool layer", layer);
+    if (layer > P->forwarded_upto) return fail(IST_ERR_STATE, "layer %d has not been computed (forward ran to %d)", layer, P->forwarded_upto);
+    u8_nhwc_to_nchw_kernel<<<ew_grid(L.out_elems, 256), 256, 0, (cudaStream_t)stream>>>(L.pool_idx, out_dev, P->NB, L.C, L.H * L.W);
+    IST_CUDA(cudaGetLastError());
+    return IST_OK;
+}
+
 int ist_plan_gram(ist_plan* P, int layer, float* out_dev, void* stream) {
     if (P == nullptr || out_dev == nullptr || layer < 0 || layer >= (int)P->layers.size()) return fail(IST_ERR_ARG, "ist_plan_gram: bad argument");
+    DeviceGuard dg(P->device);
     if (layer > P->forwarded_upto) return fail(IST_ERR_STATE, "layer %d has not been computed", layer);
     cudaStream_t st = (cudaStream_t)stream;
     Layer& L = P->layers[layer];
@@ -619,6 +646,7 @@ int ist_plan_set_loss(ist_plan* P, int n_style, const int* style_layers, const f
                       const int* content_layers, const float* content_weights) {
     if (P == nullptr || n_style < 0 || n_content < 0 || n_style > 8 || n_content > 4 || n_style + n_content > kMaxLoss)
         return fail(IST_ERR_ARG, "ist_plan_set_loss: at most 8 style and 4 content layers");
+    DeviceGuard dg(P->device);
     for (Layer& L : P->layers) { L.style_slot = -1; L.content_slot = -1; }
     P->style_layers.clear(); P->content_layers.clear();
     for (int k = 0; k < n_style; ++k) {
@@ -648,6 +676,7 @@ int ist_plan_set_loss(ist_plan* P, int n_style, const int* style_layers, const f
 
 int ist_plan_set_style_target(ist_plan* P, int style_slot, const float* gram_dev, void* stream) {
     if (P == nullptr || gram_dev == nullptr || style_slot < 0 || style_slot >= P->n_style) return fail(IST_ERR_ARG, "ist_plan_set_style_target: bad slot");
+    DeviceGuard dg(P->device);
     Layer& L = P->layers[P->style_layers[style_slot]];
     IST_CUDA(cudaMemcpyAsync(L.target, gram_dev, (size_t)L.C * L.C * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     L.target_set = true;
@@ -656,6 +685,7 @@ int ist_plan_set_style_target(ist_plan* P, int style_slot, const float* gram_dev
 
 int ist_plan_capture_content_target(ist_plan* P, int content_slot, void* stream) {
     if (P == nullptr || content_slot < 0 || content_slot >= P->n_content) return fail(IST_ERR_ARG, "ist_plan_capture_content_target: bad slot");
+    DeviceGuard dg(P->device);
     const int l = P->content_layers[content_slot];
     if (l > P->forwarded_upto) return fail(IST_ERR_STATE, "content layer %d has not been computed", l);
     Layer& L = P->layers[l];
@@ -668,6 +698,7 @@ int ist_plan_capture_content_target(ist_plan* P, int content_slot, void* stream)
 
 int ist_plan_loss_and_grad(ist_plan* P, const float* x_dev, float* grad_dev, float* losses_dev, void* stream) {
     if (P == nullptr || x_dev == nullptr || grad_dev == nullptr || losses_dev == nullptr) return fail(IST_ERR_ARG, "ist_plan_loss_and_grad: null argument");
+    DeviceGuard dg(P->device);
     const int deepest = deepest_loss_layer(P);
     if (deepest < 0) return fail(IST_ERR_STATE, "no loss configured (ist_plan_set_loss)");
     cudaStream_t st = (cudaStream_t)stream;
@@ -698,6 +729,7 @@ int ist_plan_loss_and_grad(ist_plan* P, const float* x_dev, float* grad_dev, flo
 
 int ist_plan_backward(ist_plan* P, int n_seeds, const int* layers, const float* const* seeds_dev, float* grad_dev, void* stream) {
     if (P == nullptr || n_seeds < 1 || layers == nullptr || seeds_dev == nullptr || grad_dev == nullptr) return fail(IST_ERR_ARG, "ist_plan_backward: bad argument");
+    DeviceGuard dg(P->device);
     cudaStream_t st = (cudaStream_t)stream;
     for (Layer& L : P->layers) L.ext_active = false;
     int deepest = -1;
@@ -724,6 +756,7 @@ int ist_plan_backward(ist_plan* P, int n_seeds, const int* layers, const float* 
 // internal hooks for ist_lbfgs.cu / ist_ops.cu
 namespace ist {
 int plan_batch(const ist_plan* P) { return P->NB; }
+int plan_device(const ist_plan* P) { return P->device; }
 int plan_image_elems(const ist_plan* P) { return 3 * P->H * P->W; }
 int plan_n_losses(const ist_plan* P) { return P->n_style + P->n_content; }
 void plan_set_pdl_first(ist_plan* P, bool on) { P->pdl_first = on; }

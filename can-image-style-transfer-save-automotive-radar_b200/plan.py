@@ -92,6 +92,25 @@ class Plan:
         _lib.check(self.lib.ist_plan_get_feature(self.h, self.out_index[key], _lib.ptr(out), _lib.stream_ptr()))
         return out
 
+    def pool_index(self, key):
+        """uint8 [batch,C,h,w]: window position 0..3 each pooled element of pool layer `key` took its maximum from in the last
+        forward (first maximum in row-major order), 4 where the pooled value is not positive."""
+        c, h, w = self.feature_shape(key)
+        out = torch.empty(self.batch, c, h, w, device=self.device, dtype=torch.uint8)
+        _lib.check(self.lib.ist_plan_get_pool_index(self.h, self.out_index[key], _lib.ptr(out, torch.uint8), _lib.stream_ptr()))
+        return out
+
+    def masks(self, upto_key):
+        """Every discontinuous decision of the last forward up to `upto_key`, in the oracle's `forward_masks` layout:
+        {relu name: bool sign map [batch,C,h,w], pool name: uint8 argmax position}."""
+        out = {}
+        for l in self.layers:
+            key = l[4]
+            out[key] = self.feature(key) > 0 if l[0] == _lib.LAYER_CONV3X3_RELU else self.pool_index(key)
+            if key == upto_key:
+                break
+        return out
+
     def gram(self, key):
         c, _, _ = self.feature_shape(key)
         out = torch.empty(self.batch, c, c, device=self.device, dtype=torch.float32)

@@ -48,6 +48,11 @@ int ist_version(void);
 /* 0 when the current CUDA device can run the kernels (compute capability 10.x), IST_ERR_DEVICE otherwise. */
 int ist_device_check(void);
 
+/* run-time kernel selection for the conv1_1 kernels (same effect as the IST_B200_CFF / IST_B200_CFD environment variables,
+ * but switchable inside one process so that the parity tests cover both variants): "first_conv_fwd_tc",
+ * "first_conv_dgrad_tc": 1 = tensor-core kernel (default), 0 = CUDA-core kernel. Applies to plans and per-op entry points. */
+int ist_set_option(const char* name, int value);
+
 /* kernels launched by this library in this process so far (kernels inside a replayed CUDA graph are counted per replay) */
 unsigned long long ist_launch_count(void);
 /* per-launch profiling for benchmarks: between begin and end every kernel launched eagerly (not through a graph) is
@@ -73,6 +78,11 @@ int ist_plan_forward(ist_plan* plan, const float* x_dev, int upto_layer, void* s
 /* copy the output of `layer` (after ReLU / after pool) out as fp32 NCHW [batch,C,h,w] */
 int ist_plan_get_feature(ist_plan* plan, int layer, float* out_dev, void* stream);
 int ist_plan_feature_shape(const ist_plan* plan, int layer, int* C, int* h, int* w);
+/* the decisions nn.MaxPool2d(2,2) took in the last forward (IST/model/meta_arch/vgg.py:54): for the pool layer `layer`,
+ * one byte per pooled element as NCHW [batch,C,h,w]: window position 0..3 (row-major, first maximum) that max_pool2d's
+ * backward routes the gradient to, or 4 where the pooled value is not positive (the ReLU below stops the gradient).
+ * Together with ist_plan_get_feature (> 0 = ReLU sign map) this exposes every discontinuous decision of the forward. */
+int ist_plan_get_pool_index(ist_plan* plan, int layer, uint8_t* out_dev, void* stream);
 /* GramMatrix.forward (IST/model/meta_arch/gram_matrix.py:6-11) of the current features of `layer`: out [batch,C,C] */
 int ist_plan_gram(ist_plan* plan, int layer, float* out_dev, void* stream);
 
@@ -109,6 +119,24 @@ int ist_lbfgs_reset(ist_lbfgs* opt, void* stream);
 int ist_lbfgs_step(ist_lbfgs* opt, float* x_dev, int* evals_out, float* loss_out, void* stream);
 /* per-frame losses of the most recent closure evaluation: [batch, n_losses+1] */
 int ist_lbfgs_last_losses(ist_lbfgs* opt, float* losses_host);
+
+/* per-frame optimiser state after the last ist_lbfgs_step (frames of a batch stop independently): state['func_evals'],
+ * state['n_iter'], len(old_dirs), whether the frame was still iterating when the step ended, closure evaluations this step */
+int ist_lbfgs_frame_state(ist_lbfgs* opt, int frame, int* func_evals, int* n_iter, int* hist_len, int* active, int* step_evals);
+
+/* diagnostics for the parity tests of the optimiser (torch/optim/lbfgs.py:333-537 as used by IST/model/engine/utils.py:24,43) */
+/* Record every closure evaluation: x_dev/g_dev/d_dev [capacity][batch][n] receive the evaluation point, the gradient the
+ * closure returned and the direction computed from it; scalars_dev [capacity][batch][16] doubles = loss, direction computed
+ * (0/1), still active, n_iter, history length, ring head, pair accepted (ys > 1e-10), H_diag, t, g.d, y.s, y.y, x updated,
+ * func_evals, evaluations this step, ring slot of the new pair. Call before the first step. */
+int ist_lbfgs_set_trace(ist_lbfgs* opt, float* x_dev, float* g_dev, float* d_dev, double* scalars_dev, int capacity);
+int ist_lbfgs_trace_count(ist_lbfgs* opt, int* count_host);
+/* the same optimiser on a closed-form separable objective instead of a plan's closure — per frame
+ * f(x) = sum_i 0.5 a_i (x_i - b_i)^2 + c_i cos(x_i), a/b/c [batch][n] — to drive it through rejected curvature pairs
+ * and every tolerance exit against a float64 restatement of torch's algorithm */
+int ist_lbfgs_create_test(ist_lbfgs** out, int batch, int n, const float* a_dev, const float* b_dev, const float* c_dev,
+                          int history_size, int max_iter, int max_eval, float lr, double tolerance_grad,
+                          double tolerance_change);
 
 /* image pre/post-processing on the device ------------------------------------------------------- */
 /* 8-bit images are RGB, HWC, [batch,H,W,3] uint8 on the device; network images fp32 NCHW [batch,3,H,W] in the reference's

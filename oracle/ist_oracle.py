@@ -105,6 +105,82 @@ def loss_and_grad(state, x, targets, **kw):
     return [float(l.detach()) for l in ll], float(loss.detach()), xg.grad.detach()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Flip-aware parity (SURVEY 7.3 H1 / 8d "Parity protocol"): the image gradient is discontinuous in the forward activations
+# through the ReLU sign maps and the max-pool argmax maps, so parity is reported as (i) the number of mask mismatches between
+# two forwards and (ii) the gradient of the SAME closure evaluated with the masks imposed from outside — with equal masks
+# the closure is a smooth function of its inputs and the remaining difference is kernel arithmetic alone.
+# ---------------------------------------------------------------------------------------------------------------------
+def _last_needed(keys):
+    return max(OUT_SEQ.index(k) for k in keys)
+
+
+def forward_masks(state, x, upto='relu5_1'):
+    """The decisions vgg.py:52,54 take on x: {relu name: bool [b,C,H,W] (conv output > 0), pool name: uint8 [b,C,H/2,W/2]
+    window position 0..3 (row-major, first maximum wins as in ATen's max_pool2d) or 4 where the pooled value is not
+    positive (all four inputs are masked by the preceding ReLU; no gradient passes)}."""
+    masks = {}
+    prev = x
+    for i in range(OUT_SEQ.index(upto) + 1):
+        name = FORWARD_SEQ[i]
+        if name.find('conv') != -1:
+            prev = F.relu(F.conv2d(prev, state[name + '.weight'], state[name + '.bias'], padding=1))
+            masks[OUT_SEQ[i]] = prev > 0
+        else:
+            h, w = prev.shape[2], prev.shape[3]
+            prev, idx = F.max_pool2d(prev, kernel_size=2, stride=2, return_indices=True)
+            ho, wo = prev.shape[2], prev.shape[3]
+            iy, ix = idx // w, idx % w
+            yo = torch.arange(ho, device=x.device).view(1, 1, ho, 1)
+            xo = torch.arange(wo, device=x.device).view(1, 1, 1, wo)
+            pos = ((iy - 2 * yo) * 2 + (ix - 2 * xo)).to(torch.uint8)
+            masks[OUT_SEQ[i]] = torch.where(prev > 0, pos, torch.full_like(pos, 4))
+    return masks
+
+
+def mask_mismatches(a, b):
+    """{layer: (mismatching units, units)} between two mask sets of forward_masks layout. A pool unit whose pooled value is
+    not positive on both sides (code 4) matches whatever the positions."""
+    out = {}
+    for k in a:
+        if k not in b:
+            continue
+        out[k] = (int((a[k] != b[k]).sum()), a[k].numel())
+    return out
+
+
+def vgg_forward_masked(state, x, masks, out_keys):
+    """vgg.py:44-58 with the decisions imposed: relu(y) -> y * mask, max-pool -> the window element at the given position
+    (code 4 reads position 0: its gradient is stopped by the ReLU mask of the layer below, which is all-zero there)."""
+    outputs = {}
+    prev = x
+    for i in range(_last_needed(out_keys) + 1):
+        name = FORWARD_SEQ[i]
+        if name.find('conv') != -1:
+            y = F.conv2d(prev, state[name + '.weight'], state[name + '.bias'], padding=1)
+            outputs[OUT_SEQ[i]] = y * masks[OUT_SEQ[i]].to(y.dtype)
+        else:
+            b, c, h, w = prev.shape
+            ho, wo = h // 2, w // 2
+            win = prev[:, :, :2 * ho, :2 * wo].reshape(b, c, ho, 2, wo, 2).permute(0, 1, 2, 4, 3, 5).reshape(b, c, ho, wo, 4)
+            pos = masks[OUT_SEQ[i]].to(torch.int64).clamp(max=3).unsqueeze(-1)
+            outputs[OUT_SEQ[i]] = torch.gather(win, 4, pos).squeeze(-1)
+        prev = outputs[OUT_SEQ[i]]
+    return [outputs[k] for k in out_keys]
+
+
+def loss_and_grad_masked(state, x, targets, masks, style_layers=STYLE_LAYERS, content_layers=CONTENT_LAYERS, weights=None):
+    """loss_and_grad (utils.py:29-41) with the ReLU / pool decisions of `masks` instead of the ones x itself would take."""
+    weights = weights if weights is not None else STYLE_WEIGHTS + CONTENT_WEIGHTS
+    xg = x.detach().clone().requires_grad_(True)
+    outs = vgg_forward_masked(state, xg, masks, list(style_layers) + list(content_layers))
+    fns = [gram_mse_loss] * len(style_layers) + [F.mse_loss] * len(content_layers)
+    ll = [weights[a] * fns[a](A, targets[a]) for a, A in enumerate(outs)]
+    loss = sum(ll)
+    loss.backward()
+    return [float(l.detach()) for l in ll], float(loss.detach()), xg.grad.detach()
+
+
 def optimize(state, content_image, style_image, optimized_image, max_iterations, full=True, trace=None, **kw):
     """utils.py:17-45 with torch.optim.LBFGS defaults. `optimized_image` is a leaf tensor updated in place.
     `trace`, if a list, receives (eval index, total loss) per closure evaluation."""
@@ -136,6 +212,7 @@ class LbfgsRestated:
         self.max_eval = max_eval if max_eval is not None else max_iter * 5 // 4
         self.tolerance_grad, self.tolerance_change, self.history_size = tolerance_grad, tolerance_change, history_size
         self.state = {'func_evals': 0, 'n_iter': 0}
+        self.log = None      # set to a list to receive one dict per iteration: n_iter, d, t, H_diag, ys, accepted, hist, gtd, applied
 
     def step(self, x, closure):
         """x: flat tensor updated in place; closure() -> (loss float, flat grad tensor) evaluated at the current x."""
@@ -153,6 +230,7 @@ class LbfgsRestated:
         while n_iter < self.max_iter:
             n_iter += 1
             st['n_iter'] += 1
+            ys, accepted = None, False
             if st['n_iter'] == 1:
                 d = flat_grad.neg()
                 old_dirs, old_stps, ro = [], [], []
@@ -161,6 +239,7 @@ class LbfgsRestated:
                 y = flat_grad.sub(prev_flat_grad)
                 s = d.mul(t)
                 ys = float(y.dot(s))
+                accepted = ys > 1e-10
                 if ys > 1e-10:
                     if len(old_dirs) == self.history_size:
                         old_dirs.pop(0); old_stps.pop(0); ro.pop(0)
@@ -183,6 +262,9 @@ class LbfgsRestated:
             else:
                 t = self.lr
             gtd = float(flat_grad.dot(d))
+            if self.log is not None:
+                self.log.append(dict(n_iter=st['n_iter'], d=d.clone(), t=t, H_diag=H_diag, ys=ys, accepted=accepted,
+                                     hist=len(old_dirs), gtd=gtd, applied=not (gtd > -self.tolerance_change)))
             if gtd > -self.tolerance_change:
                 break
             x.add_(d, alpha=t)

@@ -31,16 +31,31 @@ def conv_dgrad(lib, dy, w, cin, passes=3):
     return dx
 
 
-@pytest.mark.parametrize("nb,h,w", [(1, 32, 32), (2, 24, 40), (1, 7, 9), (1, 1, 1)])
-def test_first_conv(lib, nb, h, w):
+@pytest.mark.parametrize("tc", [1, 0])
+@pytest.mark.parametrize("nb,h,w", [(1, 32, 32), (2, 24, 40), (1, 7, 9), (1, 1, 1), (1, 37, 90), (2, 70, 52), (1, 129, 17)])
+def test_first_conv(lib, nb, h, w, tc):
+    """conv1_1 forward / data-gradient through the dispatch the plan uses: tc = 1 the shipped tensor-core kernels
+    (conv_first_fwd_tc_kernel, conv_first_dgrad_tc_kernel), tc = 0 the CUDA-core kernels (IST_B200_CFF / CFD = cuda);
+    sizes include non-multiples of the 16 x 8 pixel tile."""
     strict_fp32()
-    g = torch.Generator().manual_seed(1)
-    x, wt, b = randn(g, nb, 3, h, w, scale=60.0), randn(g, 64, 3, 3, 3, scale=0.27), randn(g, 64, scale=0.5)
-    ref = F.relu(F.conv2d(x.double(), wt.double(), b.double(), padding=1))
-    assert rel_l2(conv_fwd(lib, x, wt, b), ref) < 6e-7
-    dy = randn(g, nb, 64, h, w)
-    refd = torch.nn.grad.conv2d_input(x.double().shape, wt.double(), dy.double(), padding=1)
-    assert rel_l2(conv_dgrad(lib, dy, wt, 3), refd) < 5e-5
+    _lib.check(lib.ist_set_option(b"first_conv_fwd_tc", tc))
+    _lib.check(lib.ist_set_option(b"first_conv_dgrad_tc", tc))
+    try:
+        g = torch.Generator().manual_seed(1)
+        x, wt, b = randn(g, nb, 3, h, w, scale=60.0), randn(g, 64, 3, 3, 3, scale=0.27), randn(g, 64, scale=0.5)
+        ref = F.relu(F.conv2d(x.double(), wt.double(), b.double(), padding=1))
+        n0 = lib.ist_launch_count()
+        y = conv_fwd(lib, x, wt, b)
+        assert rel_l2(y, ref) < 6e-7
+        pre = F.conv2d(x.double(), wt.double(), b.double(), padding=1)
+        assert int((((y > 0) != (pre > 0)) & (pre.abs() > 1e-4 * pre.abs().max())).sum()) == 0
+        dy = randn(g, nb, 64, h, w)
+        refd = torch.nn.grad.conv2d_input(x.double().shape, wt.double(), dy.double(), padding=1)
+        assert rel_l2(conv_dgrad(lib, dy, wt, 3), refd) < 5e-5
+        assert lib.ist_launch_count() > n0
+    finally:
+        _lib.check(lib.ist_set_option(b"first_conv_fwd_tc", 1))
+        _lib.check(lib.ist_set_option(b"first_conv_dgrad_tc", 1))
 
 
 @pytest.mark.parametrize("nb,cin,cout,h,w", [
