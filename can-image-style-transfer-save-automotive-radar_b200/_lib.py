@@ -12,6 +12,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libist_b200.so")
+_LIB_OVERRIDE = os.environ.get("IST_B200_LIB")      # A/B runs of two builds on one GPU box (tools only)
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "ist_b200.h")
 
 NVCC_FLAGS = [
@@ -122,8 +123,10 @@ def load():
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
             "This package has no CPU / PyTorch fallback for the style-transfer path.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(_LIB_OVERRIDE if _LIB_OVERRIDE else LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if _LIB_OVERRIDE and not hasattr(lib, name):
+            continue                      # an older build compared A/B may lack the newest entry points
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
@@ -141,9 +144,11 @@ def check(rc):
         raise IstError(f"ist_b200 error {rc}: {msg.decode() if msg else '?'}")
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on `device` (default: the current device). Objects bound to a device (plans,
+    optimisers) pass their own device, so a plan on cuda:1 works while cuda:0 is current (the C side switches devices itself)."""
     import torch
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def ptr(t, dtype=None):

@@ -198,6 +198,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     if (dbg != nullptr && threadIdx.x == 0) {
         dbg[0] = clock64();
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+        dbg[2] = (long long)gt0;                  // absolute start of this CTA (ns): the host prints the launch stagger
     }
 
     pdl_trigger();       // the next kernel of the stream may be scheduled as SMs free up (it waits for this grid itself)
@@ -381,7 +382,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         timed_wait(bfull(bs), bph, 1);
                         tc_fence_after();
                         if (elect_one()) {
-                            if (dbg != nullptr && first) dbg[2] = clock64();
                             const uint32_t d_main = tmem_base + mb * N_TILE;
                             const uint32_t a_lo = a_lo_stage + (uint32_t)((ky * Cfg::PW + kx) * 8);
                             const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
@@ -391,7 +391,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                             if (chain_end) commit(mfull(mb));
                             commit(bempty(bs));
                             if (last_tap) commit(aempty(as));
-                            if (dbg != nullptr) dbg[3] = clock64();
                         }
                         __syncwarp();
                         first = false;
@@ -702,6 +701,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         unsigned long long gt1;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
         dbg[7] = (long long)(gt1 - gt0);          // nanoseconds: with dbg[6] - dbg[0] gives the SM clock actually running
+        dbg[3] = (long long)gt1;                  // absolute end of this CTA (ns)
     }
     if (warp == 1) {
         tc_fence_after();

@@ -327,8 +327,14 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
         double ns = 0;
         double wsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // barrier wait cycles per role (leader CTAs for the issuers)
         int nlead = 0;
+        long long gmin = h[2], gmax_start = h[2], gend = h[3];
         for (int c = 0; c < grid; ++c) {
-            for (int k = 1; k < 7; ++k) sum[k] += (double)(h[16 * c + k] - h[16 * c]);
+            if (h[16 * c + 2] < gmin) gmin = h[16 * c + 2];
+            if (h[16 * c + 2] > gmax_start) gmax_start = h[16 * c + 2];
+            if (h[16 * c + 3] > gend) gend = h[16 * c + 3];
+        }
+        for (int c = 0; c < grid; ++c) {
+            for (int k = 1; k < 7; ++k) if (k != 2 && k != 3) sum[k] += (double)(h[16 * c + k] - h[16 * c]);
             ns += (double)h[16 * c + 7];
             const bool lead = !PAIR || (c % 2 == 0);
             if (lead) ++nlead;
@@ -336,9 +342,9 @@ inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtenso
         }
         fprintf(stderr, "[dbg-wait] avg cycles waiting | issuer1: acc-empty %.0f B-full %.0f A-full %.0f | issuer2: operands %.0f cross-empty %.0f | producer: A-empty %.0f B-empty %.0f | epilogue warp 2: acc-full %.0f\n",
                 wsum[0] / nlead, wsum[1] / nlead, wsum[2] / nlead, wsum[3] / nlead, wsum[4] / nlead, wsum[5] / grid, wsum[6] / grid, wsum[7] / grid);
-        fprintf(stderr, "[dbg] conv %dx%d %d->%d taps %d passes %d promote %d grid %d tiles %d | avg clk since entry: setup %.0f first_mma %.0f last_issue %.0f acc_read %.0f stored %.0f exit %.0f | %.1f us -> SM clock %.0f MHz\n",
-                p.H, p.W, p.Cin, p.Cout, p.taps, p.passes, p.promote, grid, total, sum[1] / grid, sum[2] / grid, sum[3] / grid,
-                sum[4] / grid, sum[5] / grid, sum[6] / grid, ns / grid * 1e-3, sum[6] / ns * 1e3);
+        fprintf(stderr, "[dbg] conv %dx%d %d->%d taps %d passes %d promote %d grid %d tiles %d | avg clk since entry: setup %.0f acc_read %.0f stored %.0f exit %.0f | CTA life %.1f us -> SM clock %.0f MHz | first CTA start -> last CTA start %.1f us, first start -> last exit %.1f us\n",
+                p.H, p.W, p.Cin, p.Cout, p.taps, p.passes, p.promote, grid, total, sum[1] / grid,
+                sum[4] / grid, sum[5] / grid, sum[6] / grid, ns / grid * 1e-3, sum[6] / ns * 1e3, (gmax_start - gmin) * 1e-3, (gend - gmin) * 1e-3);
         launch_post(st);
         return IST_OK;
     }

@@ -28,6 +28,7 @@ int plan_n_losses(const ist_plan* P);
 void plan_set_pdl_first(ist_plan* P, bool on);
 
 constexpr int LB_MAXH = 112;          // history_size must be < LB_MAXH (shared-memory budget of the solve kernel)
+constexpr int LB_LDG = LB_MAXH + 1;   // leading dimension of the dot-product matrices (odd: bank-conflict-free column walks in shared memory)
 constexpr int LB_WT = 512;            // elements per warp-tile (16 per lane)
 constexpr int LB_NSTAT = 8;           // ys, yy, s.g, y.g, g.g, |g|_1, max|g|, (unused)
 constexpr int LB_PART = LB_MAXH * 5 + LB_NSTAT;
@@ -38,9 +39,10 @@ struct LbFrame {
     double H_diag, t, prev_loss, orig_loss, loss, gtd;
     double ro[LB_MAXH];
     // outputs of the solve for the update pass
-    float cg, cy_new, cs_new, t_f, t_prev_f;
+    float cg, t_f, t_prev_f;                // cg != 0 marks "an iteration was computed" (lbfgs_update_kernel)
+    double cg_d, cy_new, cs_new;            // coefficients of d in float64: d = cg*g + cy_new*y_new + cs_new*s_new + sum ...
     int read_slot[LB_MAXH];
-    float read_cy[LB_MAXH], read_cs[LB_MAXH];
+    double read_cy[LB_MAXH], read_cs[LB_MAXH];
 };
 
 struct LbParams {
@@ -58,8 +60,8 @@ struct LbParams {
     double* part;                 // [NB][nblk][LB_PART]
     double* tot;                  // [NB][LB_PART] fixed-order sums (max for the |g| entry) of `part`
     float* dmax_part;             // [NB][nblk]
-    double* SY;                   // [NB][LB_MAXH][LB_MAXH]  s_i.y_j by physical slot
-    double* YY;                   // [NB][LB_MAXH][LB_MAXH]
+    double* SY;                   // [NB][LB_MAXH][LB_LDG]  s_i.y_j by physical slot
+    double* YY;                   // [NB][LB_MAXH][LB_LDG]
     LbFrame* frames;              // [NB]
     int it;                       // 1-based iteration index inside this step()
     int max_iter, max_eval;
@@ -67,6 +69,15 @@ struct LbParams {
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// float64 shuffle tree: the per-lane partial sums (16 fp32 products each) are added exactly from here on. With an fp32 tree the
+// dot products of a 512-element tile carried ~3e-7 of sum|a_i b_i|; near-orthogonal history vectors amplify that through the
+// two-loop recursion (tools/lbfgs_rounding_study.py: direction error vs float64 2.6e-5 -> 3e-6 together with the float64
+// accumulation of d in lbfgs_update_kernel; torch's own fp32 arithmetic sits at 9e-6).
+__device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -181,10 +192,11 @@ lbfgs_dots_kernel(const LbParams P) {
                 a5 += fabsf(gv[e]);
                 gmax = fmaxf(gmax, fabsf(gv[e]));
             }
-            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4); a5 = warp_sum(a5);
+            const double b0 = warp_sum_d((double)a0), b1 = warp_sum_d((double)a1), b2 = warp_sum_d((double)a2);
+            const double b3 = warp_sum_d((double)a3), b4 = warp_sum_d((double)a4), b5 = warp_sum_d((double)a5);
             if (lane == 0) {
                 double* st = &wacc[warp][5 * LB_MAXH];
-                st[0] += a0; st[1] += a1; st[2] += a2; st[3] += a3; st[4] += a4; st[5] += a5;
+                st[0] += b0; st[1] += b1; st[2] += b2; st[3] += b3; st[4] += b4; st[5] += b5;
             }
             for (int i = 0; i < hist; ++i) {
                 const int slot = slot_of(i);
@@ -221,10 +233,11 @@ lbfgs_dots_kernel(const LbParams P) {
                     c3 = fmaf(s_i[e], gv[e], c3);   // s_i . g
                     c4 = fmaf(y_i[e], gv[e], c4);   // y_i . g
                 }
-                c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); c3 = warp_sum(c3); c4 = warp_sum(c4);
+                const double e0 = warp_sum_d((double)c0), e1 = warp_sum_d((double)c1), e2 = warp_sum_d((double)c2);
+                const double e3 = warp_sum_d((double)c3), e4 = warp_sum_d((double)c4);
                 if (lane == 0) {
                     double* a = &wacc[warp][slot * 5];
-                    a[0] += c0; a[1] += c1; a[2] += c2; a[3] += c3; a[4] += c4;
+                    a[0] += e0; a[1] += e1; a[2] += e2; a[3] += e3; a[4] += e4;
                 }
             }
             if (vec) used += (uint32_t)hist;
@@ -282,15 +295,18 @@ lbfgs_reduce_kernel(const LbParams P) {
 // pass 2: scalar logic of one iteration of LBFGS.step for one frame (one CTA of LB_SOLVE_THREADS threads).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int LB_SOLVE_THREADS = 512;
-inline __host__ __device__ int lb_ld(int m) { return m + 1; }   // padded leading dimension of the smem matrices
-inline size_t lb_solve_smem(int m) { return 2 * (size_t)m * lb_ld(m) * sizeof(double); }
+// dynamic shared memory of the solve: physical-slot copies of SY and YY, rows 0 .. m-1 (the ring only uses slots < m)
+// (an even number of rows keeps both copies 16-byte aligned and sized, as cp.async.bulk needs)
+inline __host__ __device__ int lb_rows(int m) { return (m + 1) & ~1; }
+inline size_t lb_solve_smem(int m) { return 2 * (size_t)lb_rows(m) * LB_LDG * sizeof(double) + 16; }
 
 __global__ void __launch_bounds__(LB_SOLVE_THREADS)
 lbfgs_solve_kernel(const LbParams P) {
-    extern __shared__ double sm[];
-    const int LB_LD = lb_ld(P.m);
-    double* SYs = sm;                          // [m][LB_LD] logical order: SYs[i][j] = s_i . y_j
-    double* YYs = sm + (size_t)P.m * LB_LD;    // [m][LB_LD]
+    extern __shared__ __align__(16) double sm[];
+    constexpr int LB_LD = LB_LDG;
+    double* SYs = sm;                          // [m][LB_LDG] by PHYSICAL slot: SYs[p][q] = s_p . y_q
+    double* YYs = sm + (size_t)lb_rows(P.m) * LB_LD;    // [m][LB_LDG]
+    __shared__ __align__(8) unsigned long long copy_bar;
     __shared__ double tot[LB_PART];
     __shared__ double al_s[LB_MAXH], c_s[LB_MAXH], sg_s[LB_MAXH], yg_s[LB_MAXH];
     __shared__ double red[LB_MAXH];
@@ -299,84 +315,115 @@ lbfgs_solve_kernel(const LbParams P) {
     pdl_trigger();
     pdl_wait();
     LbFrame& F = P.frames[b];
-    double* SYg = P.SY + (size_t)b * LB_MAXH * LB_MAXH;
-    double* YYg = P.YY + (size_t)b * LB_MAXH * LB_MAXH;
+    double* SYg = P.SY + (size_t)b * LB_MAXH * LB_LDG;
+    double* YYg = P.YY + (size_t)b * LB_MAXH * LB_LDG;
+    // The dot-product matrices of the previous iterations come in as two 1-D bulk copies (m * 113 doubles each, ~90 KB at
+    // m = 100) that overlap the scalar logic below. Gathering them element by element in logical order (the previous form)
+    // was a chain of ~20 dependent L2 round trips per thread: 30 of the solve's 39 us at full history.
+    const uint32_t mat_bytes = (uint32_t)((size_t)lb_rows(m) * LB_LDG * sizeof(double));
+    const uint32_t bar = smem_u32(&copy_bar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        mbar_arrive_expect_tx(bar, 2 * mat_bytes);
+        bulk_load_1d(smem_u32(SYs), SYg, mat_bytes, bar);
+        bulk_load_1d(smem_u32(YYs), YYg, mat_bytes, bar);
+    }
 
     for (int i = tid; i < LB_PART; i += blockDim.x) tot[i] = P.tot[(size_t)b * LB_PART + i];
     __syncthreads();
     const double* st = &tot[5 * LB_MAXH];
     const double ys = st[0], yy = st[1], sg_new = st[2], yg_new = st[3], gg = st[4], g1 = st[5], gmax = st[6];
 
+    // max |d| of the previous update pass: per-CTA maxima reduced by the whole CTA (thread 0 walking up to 296 values alone was a
+    // chain of L2 round trips, most of the solve's 39 us)
+    __shared__ float sh_dm[LB_SOLVE_THREADS / 32];
+    {
+        float dmv = 0.f;
+        for (int k = tid; k < P.nblk; k += blockDim.x) dmv = fmaxf(dmv, P.dmax_part[(size_t)b * P.nblk + k]);
+        dmv = warp_max(dmv);
+        if ((tid & 31) == 0) sh_dm[tid >> 5] = dmv;
+    }
+    __syncthreads();
+    // The frame state lives in global memory: thread 0 reads every scalar it needs up front (independent loads, one L2 round
+    // trip), decides on registers and writes the changed fields back once — a read-modify-write per field interleaved with the
+    // control flow was a chain of ~20 dependent L2 round trips.
+    __shared__ int sh_head, sh_accepted, sh_new_slot, sh_n_iter;
+    __shared__ double sh_H, sh_loss;
     if (tid == 0) {
         const double loss = (double)P.losses[(size_t)b * P.loss_stride + P.loss_total];
-        int go = 1;
+        int n_iter = F.n_iter, func_evals = F.func_evals, hist_len = F.hist_len, head = F.head, active = F.active;
+        int current_evals = F.current_evals;
+        double H_diag = F.H_diag;
+        const double t_prev = F.t, prev_loss = F.prev_loss;
+        int go = 1, accepted = 0, new_slot = 0;
+        const bool evaluated = (P.it == 1) || active != 0;      // this closure evaluation counts for the frame
         if (P.it == 1) {                        // lbfgs.py:364-374: first closure of step()
-            F.active = 1;
-            F.current_evals = 1;
-            F.func_evals += 1;
+            active = 1;
+            current_evals = 1;
+            func_evals += 1;
             F.orig_loss = loss;
-            F.loss = loss;
-            if (gmax <= P.tol_grad) { F.active = 0; go = 0; }
-        } else if (F.active) {                  // lbfgs.py:493-523: the checks that follow the re-evaluation
-            F.current_evals += 1;
-            F.func_evals += 1;
-            F.loss = loss;
+            if (gmax <= P.tol_grad) { active = 0; go = 0; }
+        } else if (active) {                    // lbfgs.py:493-523: the checks that follow the re-evaluation
+            current_evals += 1;
+            func_evals += 1;
             float dm = 0.f;
-            for (int k = 0; k < P.nblk; ++k) dm = fmaxf(dm, P.dmax_part[(size_t)b * P.nblk + k]);
-            if (F.current_evals >= P.max_eval) go = 0;
+            for (int k = 0; k < LB_SOLVE_THREADS / 32; ++k) dm = fmaxf(dm, sh_dm[k]);
+            if (current_evals >= P.max_eval) go = 0;
             else if (gmax <= P.tol_grad) go = 0;
-            else if ((double)dm * fabs(F.t) <= P.tol_change) go = 0;
-            else if (fabs(loss - F.prev_loss) < P.tol_change) go = 0;
-            if (!go) F.active = 0;
+            else if ((double)dm * fabs(t_prev) <= P.tol_change) go = 0;
+            else if (fabs(loss - prev_loss) < P.tol_change) go = 0;
+            if (!go) active = 0;
         } else {
             go = 0;
         }
-        F.apply = 0;
-        F.accepted = 0;
-        F.nread = 0;
         if (go) {
-            F.n_iter += 1;
-            if (F.n_iter == 1) {                // lbfgs.py:396-401
-                F.hist_len = 0; F.head = 0; F.H_diag = 1.0;
+            n_iter += 1;
+            if (n_iter == 1) {                  // lbfgs.py:396-401
+                hist_len = 0; head = 0; H_diag = 1.0;
             } else if (ys > 1e-10) {            // lbfgs.py:404-420
-                int slot;
-                if (F.hist_len == m) { slot = F.head; F.head = (F.head + 1) % m; }
-                else { slot = (F.head + F.hist_len) % m; F.hist_len += 1; }
-                F.accepted = 1;
-                F.new_slot = slot;
-                F.ro[slot] = 1.0 / ys;
-                F.H_diag = ys / yy;
+                if (hist_len == m) { new_slot = head; head = (head + 1) % m; }
+                else { new_slot = (head + hist_len) % m; hist_len += 1; }
+                accepted = 1;
+                F.ro[new_slot] = 1.0 / ys;
+                H_diag = ys / yy;
             }
         }
-        sh_go = go;
-        sh_h = F.hist_len;
+        F.active = active; F.current_evals = current_evals; F.func_evals = func_evals;
+        if (evaluated) F.loss = loss;
+        F.apply = 0; F.accepted = accepted; F.nread = 0; F.new_slot = new_slot;
+        F.n_iter = n_iter; F.hist_len = hist_len; F.head = head; F.H_diag = H_diag;
+        sh_go = go; sh_h = hist_len; sh_head = head; sh_accepted = accepted; sh_new_slot = new_slot; sh_n_iter = n_iter;
+        sh_H = H_diag; sh_loss = loss;
     }
     __syncthreads();
+    mbar_wait(bar, 0);                          // the copies have landed (every thread waits: the CTA may not exit before them)
     if (!sh_go) return;
-    const int h = sh_h, head = F.head, accepted = F.accepted, new_slot = F.new_slot;
+    const int h = sh_h, head = sh_head, accepted = sh_accepted, new_slot = sh_new_slot;
     auto phys = [&](int i) { int s = head + i; return s >= m ? s - m : s; };
 
-    // fold the new pair into the physical-slot matrices (row/column new_slot)
+    // fold the new pair into the physical-slot matrices (row / column new_slot), in shared memory for this iteration and in
+    // global memory for the next ones
     if (accepted) {
         for (int i = tid; i < h; i += blockDim.x) {
             const int p = phys(i);
             if (p == new_slot) continue;
-            SYg[(size_t)p * LB_MAXH + new_slot] = tot[p * 5 + 0];      // s_i . y_new
-            SYg[(size_t)new_slot * LB_MAXH + p] = tot[p * 5 + 1];      // s_new . y_i
-            YYg[(size_t)p * LB_MAXH + new_slot] = tot[p * 5 + 2];
-            YYg[(size_t)new_slot * LB_MAXH + p] = tot[p * 5 + 2];
+            const double sy_in = tot[p * 5 + 0], sy_ni = tot[p * 5 + 1], yy_in = tot[p * 5 + 2];
+            SYs[p * LB_LD + new_slot] = sy_in;                          // s_i . y_new
+            SYs[new_slot * LB_LD + p] = sy_ni;                          // s_new . y_i
+            YYs[p * LB_LD + new_slot] = yy_in;
+            YYs[new_slot * LB_LD + p] = yy_in;
+            SYg[(size_t)p * LB_LDG + new_slot] = sy_in;
+            SYg[(size_t)new_slot * LB_LDG + p] = sy_ni;
+            YYg[(size_t)p * LB_LDG + new_slot] = yy_in;
+            YYg[(size_t)new_slot * LB_LDG + p] = yy_in;
         }
         if (tid == 0) {
-            SYg[(size_t)new_slot * LB_MAXH + new_slot] = ys;
-            YYg[(size_t)new_slot * LB_MAXH + new_slot] = yy;
+            SYs[new_slot * LB_LD + new_slot] = ys;
+            YYs[new_slot * LB_LD + new_slot] = yy;
+            SYg[(size_t)new_slot * LB_LDG + new_slot] = ys;
+            YYg[(size_t)new_slot * LB_LDG + new_slot] = yy;
         }
-    }
-    __syncthreads();
-    // logical-order copies in shared memory and the g-dots
-    for (int e = tid; e < h * h; e += blockDim.x) {
-        const int i = e / h, j = e % h;
-        SYs[i * LB_LD + j] = SYg[(size_t)phys(i) * LB_MAXH + phys(j)];
-        YYs[i * LB_LD + j] = YYg[(size_t)phys(i) * LB_MAXH + phys(j)];
     }
     for (int i = tid; i < h; i += blockDim.x) {
         const int p = phys(i);
@@ -386,31 +433,100 @@ lbfgs_solve_kernel(const LbParams P) {
     }
     __syncthreads();
 
-    // The two sequential loops run on the first 4 warps only (h <= 100 < 128), synchronised with a named barrier: a barrier
-    // over 4 warps is several times cheaper than one over the 16 warps that loaded the matrices.
-    const double H = F.H_diag;
+    // The two sequential loops of the recursion are triangular solves with R = triu(SY) (logical order, diagonal SY_ii = 1 / ro_i):
+    //   first loop  (lbfgs.py:431-436, newest to oldest):  R al = -sg                      (back substitution)
+    //   second loop (lbfgs.py:440-443, oldest to newest):  c_i = al_i - ro_i (v_i + sum_{j<i} c_j SY_ji)   (forward substitution)
+    // They run blocked on the first 4 warps (h <= 100 < 128, thread k owns unknown k): a 32 x 32 diagonal block is solved inside
+    // ONE warp with shuffles (no barrier per unknown), the off-diagonal contributions of a finished block are a small dense
+    // update by all 128 threads behind one named barrier per block. One barrier per unknown (the previous form) cost ~370 cycles
+    // x 200 unknowns = 39 us per iteration at full history.
+    const double H = sh_H;
     if (tid < 128) {
-        // first loop (lbfgs.py:431-436), newest to oldest: al_i = ro_i * s_i.q with q = -g - sum_{j>i} al_j y_j
-        const double ro_t = tid < h ? F.ro[phys(tid)] : 0.0;
-        double u = 0.0;                              // thread k: sum_{j processed} al_j * (s_k . y_j)
-        for (int i = h - 1; i >= 0; --i) {
-            if (tid == i) al_s[i] = ro_t * (-sg_s[i] - u);
+        const int lane = tid & 31, wq = tid >> 5;
+        const int nblocks = (h + 31) >> 5;
+        const int pk = tid < h ? phys(tid) : 0;                // physical slot (matrix row / column) of this thread's unknown
+        const double ro_t = tid < h ? F.ro[pk] : 0.0;
+        // FP64 instructions have a long dependent-issue latency here (~50 cycles measured through this kernel), so the chains are
+        // kept short: inside a diagonal block the unknown of lane l is carried as z_l = ro_l * (rhs_l - u_l), updated with ONE
+        // DFMA per finished unknown (row pre-scaled by ro, off the chain), so a step is shuffle + DFMA; the dense updates
+        // between blocks and the y.r product run as four independent partial sums.
+        double rhs = tid < h ? -sg_s[tid] : 0.0;              // -sg_k - sum over finished (later) blocks of al_j * SY_kj
+        for (int bb = nblocks - 1; bb >= 0; --bb) {
+            if (wq == bb) {
+                // the pre-scaled row of this lane's unknown comes into registers first (32 independent loads), so that a step of
+                // the sequential part is shuffle + DFMA only; unknowns beyond h are zeros that change nothing
+                const int lim = (h - bb * 32) < 32 ? (h - bb * 32) : 32;
+                double srow[32];
+#pragma unroll
+                for (int l = 0; l < 32; ++l) srow[l] = (lane < l && l < lim) ? -ro_t * SYs[pk * LB_LD + phys(bb * 32 + l)] : 0.0;
+                double z = ro_t * rhs, mine = 0.0;
+#pragma unroll
+                for (int l = 31; l >= 0; --l) {
+                    const double al_l = __shfl_sync(0xffffffffu, z, l);
+                    if (lane == l) mine = al_l;
+                    z = fma(al_l, srow[l], z);
+                }
+                if (tid < h) al_s[tid] = mine;
+            }
             named_bar_sync(1, 128);
-            if (tid < i) u += al_s[i] * SYs[tid * LB_LD + i];
+            if (tid < bb * 32) {
+                const int j0 = bb * 32, j1 = (bb * 32 + 32) < h ? (bb * 32 + 32) : h;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int j = j0;
+                for (; j + 4 <= j1; j += 4) {
+                    a0 = fma(al_s[j], SYs[pk * LB_LD + phys(j)], a0);
+                    a1 = fma(al_s[j + 1], SYs[pk * LB_LD + phys(j + 1)], a1);
+                    a2 = fma(al_s[j + 2], SYs[pk * LB_LD + phys(j + 2)], a2);
+                    a3 = fma(al_s[j + 3], SYs[pk * LB_LD + phys(j + 3)], a3);
+                }
+                for (; j < j1; ++j) a0 = fma(al_s[j], SYs[pk * LB_LD + phys(j)], a0);
+                rhs -= (a0 + a1) + (a2 + a3);
+            }
         }
-        named_bar_sync(1, 128);
         // r = H*q: y_k . r before the second loop
-        double v = 0.0, w = 0.0;
+        double v = 0.0;
         if (tid < h) {
-            double acc = -yg_s[tid];
-            for (int j = 0; j < h; ++j) acc -= al_s[j] * YYs[tid * LB_LD + j];
-            v = H * acc;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int j = 0;
+            for (; j + 4 <= h; j += 4) {
+                a0 = fma(al_s[j], YYs[pk * LB_LD + phys(j)], a0);
+                a1 = fma(al_s[j + 1], YYs[pk * LB_LD + phys(j + 1)], a1);
+                a2 = fma(al_s[j + 2], YYs[pk * LB_LD + phys(j + 2)], a2);
+                a3 = fma(al_s[j + 3], YYs[pk * LB_LD + phys(j + 3)], a3);
+            }
+            for (; j < h; ++j) a0 = fma(al_s[j], YYs[pk * LB_LD + phys(j)], a0);
+            v = H * (-yg_s[tid] - ((a0 + a1) + (a2 + a3)));
         }
-        // second loop (lbfgs.py:440-443), oldest to newest: be_i = ro_i * y_i.r ; r += (al_i - be_i) s_i
-        for (int i = 0; i < h; ++i) {
-            if (tid == i) c_s[i] = al_s[i] - ro_t * (v + w);
+        const double al_me = tid < h ? al_s[tid] : 0.0;
+        double w = 0.0;                                         // sum over finished (earlier) blocks of c_j * SY_jk
+        for (int bb = 0; bb < nblocks; ++bb) {
+            if (wq == bb) {
+                const int lim = (h - bb * 32) < 32 ? (h - bb * 32) : 32;
+                double scol[32];
+#pragma unroll
+                for (int l = 0; l < 32; ++l) scol[l] = (lane > l && l < lim && tid < h) ? -ro_t * SYs[phys(bb * 32 + l) * LB_LD + pk] : 0.0;
+                double q = al_me - ro_t * (v + w), mine = 0.0;   // c_k = q_k once every earlier unknown of the block is folded in
+#pragma unroll
+                for (int l = 0; l < 32; ++l) {
+                    const double c_l = __shfl_sync(0xffffffffu, q, l);
+                    if (lane == l) mine = c_l;
+                    q = fma(c_l, scol[l], q);
+                }
+                if (tid < h) c_s[tid] = mine;
+            }
             named_bar_sync(1, 128);
-            if (tid > i && tid < h) w += c_s[i] * SYs[i * LB_LD + tid];
+            if (tid >= bb * 32 + 32 && tid < h) {
+                const int j0 = bb * 32;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    a0 = fma(c_s[j0 + j], SYs[phys(j0 + j) * LB_LD + pk], a0);
+                    a1 = fma(c_s[j0 + j + 1], SYs[phys(j0 + j + 1) * LB_LD + pk], a1);
+                    a2 = fma(c_s[j0 + j + 2], SYs[phys(j0 + j + 2) * LB_LD + pk], a2);
+                    a3 = fma(c_s[j0 + j + 3], SYs[phys(j0 + j + 3) * LB_LD + pk], a3);
+                }
+                w += (a0 + a1) + (a2 + a3);
+            }
         }
     }
     __syncthreads();
@@ -420,17 +536,24 @@ lbfgs_solve_kernel(const LbParams P) {
     const int nread = accepted ? h - 1 : h;
     if (tid < nread) {
         F.read_slot[tid] = phys(tid);
-        F.read_cy[tid] = (float)(-H * al_s[tid]);
-        F.read_cs[tid] = (float)c_s[tid];
+        F.read_cy[tid] = -H * al_s[tid];
+        F.read_cs[tid] = c_s[tid];
+    }
+    __syncthreads();
+    if (tid < 32) {
+        // g.d: lane l adds red[l], red[l + 32], ... in order, then a fixed shuffle tree (deterministic)
+        double part = 0.0;
+        for (int k = tid; k < h; k += 32) part += red[k];
+        part = warp_sum_d(part);
+        if (tid == 0) red[0] = part;
     }
     __syncthreads();
     if (tid == 0) {
-        double gtd = -H * gg;
-        for (int k = 0; k < h; ++k) gtd += red[k];
+        const double gtd = -H * gg + red[0];
         F.gtd = gtd;
-        F.prev_loss = F.loss;                                            // lbfgs.py:449
+        F.prev_loss = sh_loss;                                           // lbfgs.py:449
         double t;
-        if (F.n_iter == 1) {                                             // lbfgs.py:454-457
+        if (sh_n_iter == 1) {                                            // lbfgs.py:454-457
             const float inv = 1.0f / (float)g1;
             t = (double)(inv < 1.0f ? inv : 1.0f) * P.lr;
         } else {
@@ -439,8 +562,9 @@ lbfgs_solve_kernel(const LbParams P) {
         F.t = t;
         F.t_f = (float)t;
         F.cg = (float)(-H);
-        F.cy_new = accepted ? (float)(-H * al_s[h - 1]) : 0.f;
-        F.cs_new = accepted ? (float)c_s[h - 1] : 0.f;
+        F.cg_d = -H;
+        F.cy_new = accepted ? -H * al_s[h - 1] : 0.0;
+        F.cs_new = accepted ? c_s[h - 1] : 0.0;
         F.nread = nread;
         if (gtd > -P.tol_change) { F.active = 0; F.apply = 0; }          // lbfgs.py:462-464 (break before the update)
         else F.apply = 1;
@@ -452,16 +576,42 @@ lbfgs_solve_kernel(const LbParams P) {
 // pass 3: d <- cg*g + cy_new*y_new + cs_new*s_new + sum_i cy_i*Y_i + cs_i*S_i; push (y_new, s_new); prev_g <- g;
 // x += t*d when the solve allowed it; per-CTA max|d|.
 // ---------------------------------------------------------------------------------------------------------------
+// d is a sum of up to 2m + 1 vectors with large cancellations. With fp32 coefficients and plain fp32 accumulation its distance
+// from float64 arithmetic was 3e-5 ... 1e-4 (relative L2; torch's own fp32 two-loop recursion: ~1e-5), which feeds back through
+// s = t * d into the history. The sum is therefore formed as a compensated dot product in fp32 (Ogita / Rump / Oishi "Dot2":
+// error-free product by FMA, error-free TwoSum, coefficients as fp32 hi + lo pairs) — the accuracy of a float64 accumulation
+// without float64 instructions (an F2F.F64.F32 + DFMA version made this HBM-bound pass 2x slower: 108 -> 203 us per iteration,
+// profiles/r02_lbfgs_ab.log). d is rounded to fp32 once, like torch's d.
+// (Blackwell's packed FFMA2 / FADD2 / FMUL2 forms of the same step were slower still: 208 us, profiles/r02_lbfgs_ab.log.)
+__device__ __forceinline__ void lb_dot2_step(float& hi, float& lo, float ch, float cl, float v) {
+    const float p = __fmul_rn(ch, v);
+    float pe = __fmaf_rn(ch, v, -p);                    // exact error of the product
+    pe = __fmaf_rn(cl, v, pe);                          // low part of the coefficient
+    const float s = __fadd_rn(hi, p);
+    const float bb = __fsub_rn(s, hi);
+    const float err = __fadd_rn(__fsub_rn(hi, __fsub_rn(s, bb)), __fsub_rn(p, bb));      // exact error of the sum
+    lo = __fadd_rn(lo, __fadd_rn(err, pe));
+    hi = s;
+}
+__device__ __forceinline__ void lb_split(double c, float& h, float& l) {
+    h = (float)c;
+    l = (float)(c - (double)h);
+}
+
 __global__ void __launch_bounds__(256)
 lbfgs_update_kernel(const LbParams P) {
     __shared__ float wmax[8];
     __shared__ int s_slot[LB_MAXH];
-    __shared__ float s_cy[LB_MAXH], s_cs[LB_MAXH];
+    __shared__ float s_cyh[LB_MAXH], s_cyl[LB_MAXH], s_csh[LB_MAXH], s_csl[LB_MAXH];
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const LbFrame& F = P.frames[b];
     pdl_trigger();
     pdl_wait();
-    for (int i = threadIdx.x; i < F.nread; i += blockDim.x) { s_slot[i] = F.read_slot[i]; s_cy[i] = F.read_cy[i]; s_cs[i] = F.read_cs[i]; }
+    for (int i = threadIdx.x; i < F.nread; i += blockDim.x) {
+        s_slot[i] = F.read_slot[i];
+        lb_split(F.read_cy[i], s_cyh[i], s_cyl[i]);
+        lb_split(F.read_cs[i], s_csh[i], s_csl[i]);
+    }
     __syncthreads();
     float dmax = 0.f;
     // `F.cg != 0` marks "an iteration was computed": the solve writes cg = -H_diag (never 0) and the host clears it before
@@ -473,15 +623,18 @@ lbfgs_update_kernel(const LbParams P) {
         const bool has_prev = F.n_iter >= 2;      // a previous direction exists (n_iter was already incremented)
         const float t_old_new = F.t_f;
         const int ntiles = (n + LB_WT - 1) / LB_WT;
-        const float cg = F.cg, cyn = F.cy_new, csn = F.cs_new;
+        float cgh, cgl, cynh, cynl, csnh, csnl;
+        lb_split(F.cg_d, cgh, cgl);
+        lb_split(F.cy_new, cynh, cynl);
+        lb_split(F.cs_new, csnh, csnl);
         const int nread = F.nread, accepted = F.accepted, new_slot = F.new_slot, apply = F.apply;
         for (int tile = blockIdx.x * 8 + warp; tile < ntiles; tile += gridDim.x * 8) {
             const size_t base = (size_t)tile * LB_WT;
             const int n_left = n - (int)base;
-            float gv[16], acc[16];
+            float gv[16], hi[16], lo[16];
             lb_load16(P.g + fo, base, n_left, lane, vec, gv);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) acc[e] = cg * gv[e];
+            for (int e = 0; e < 16; ++e) { hi[e] = 0.f; lo[e] = 0.f; lb_dot2_step(hi[e], lo[e], cgh, cgl, gv[e]); }
             if (has_prev) {
                 float yv[16], sv[16];
                 lb_load16(P.prev_g + fo, base, n_left, lane, vec, yv);
@@ -493,7 +646,11 @@ lbfgs_update_kernel(const LbParams P) {
                     // solve replaced F.t with the step size of the new direction
                     const float tp = F.t_prev_f;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) { sv[e] = tp * sv[e]; acc[e] = fmaf(cyn, yv[e], fmaf(csn, sv[e], acc[e])); }
+                    for (int e = 0; e < 16; ++e) {
+                        sv[e] = tp * sv[e];
+                        lb_dot2_step(hi[e], lo[e], csnh, csnl, sv[e]);
+                        lb_dot2_step(hi[e], lo[e], cynh, cynl, yv[e]);
+                    }
                     const size_t ho = ((size_t)new_slot * P.NB + b) * (size_t)n;
                     lb_store16(P.S + ho, base, n_left, lane, vec, sv);
                     lb_store16(P.Y + ho, base, n_left, lane, vec, yv);
@@ -504,19 +661,23 @@ lbfgs_update_kernel(const LbParams P) {
                 float s_i[16], y_i[16];
                 lb_load16(P.S + ho, base, n_left, lane, vec, s_i);
                 lb_load16(P.Y + ho, base, n_left, lane, vec, y_i);
-                const float cy = s_cy[i], cs = s_cs[i];
+                const float cyh = s_cyh[i], cyl = s_cyl[i], csh = s_csh[i], csl = s_csl[i];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) acc[e] = fmaf(cy, y_i[e], fmaf(cs, s_i[e], acc[e]));
+                for (int e = 0; e < 16; ++e) {
+                    lb_dot2_step(hi[e], lo[e], csh, csl, s_i[e]);
+                    lb_dot2_step(hi[e], lo[e], cyh, cyl, y_i[e]);
+                }
             }
-            lb_store16(P.d + fo, base, n_left, lane, vec, acc);
-            lb_store16(P.prev_g + fo, base, n_left, lane, vec, gv);
+            float dv[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) dmax = fmaxf(dmax, fabsf(acc[e]));
+            for (int e = 0; e < 16; ++e) { dv[e] = __fadd_rn(hi[e], lo[e]); dmax = fmaxf(dmax, fabsf(dv[e])); }
+            lb_store16(P.d + fo, base, n_left, lane, vec, dv);
+            lb_store16(P.prev_g + fo, base, n_left, lane, vec, gv);
             if (apply) {
                 float xv[16];
                 lb_load16(P.x + fo, base, n_left, lane, vec, xv);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) xv[e] = fmaf(t_old_new, acc[e], xv[e]);
+                for (int e = 0; e < 16; ++e) xv[e] = fmaf(t_old_new, dv[e], xv[e]);
                 lb_store16(P.x + fo, base, n_left, lane, vec, xv);
             }
         }
@@ -698,8 +859,8 @@ static int lbfgs_create_common(ist_lbfgs** out, ist_plan* plan, int batch, int n
     if (rc == IST_OK) rc = O->mem.alloc(&P.part, (size_t)P.NB * P.nblk_dots * LB_PART);
     if (rc == IST_OK) rc = O->mem.alloc(&P.tot, (size_t)P.NB * LB_PART);
     if (rc == IST_OK) rc = O->mem.alloc(&P.dmax_part, (size_t)P.NB * P.nblk);
-    if (rc == IST_OK) rc = O->mem.alloc(&P.SY, (size_t)P.NB * LB_MAXH * LB_MAXH);
-    if (rc == IST_OK) rc = O->mem.alloc(&P.YY, (size_t)P.NB * LB_MAXH * LB_MAXH);
+    if (rc == IST_OK) rc = O->mem.alloc(&P.SY, (size_t)P.NB * LB_MAXH * LB_LDG);
+    if (rc == IST_OK) rc = O->mem.alloc(&P.YY, (size_t)P.NB * LB_MAXH * LB_LDG);
     if (rc == IST_OK) rc = O->mem.alloc(&P.frames, (size_t)P.NB);
     if (rc == IST_OK) rc = O->mem.alloc(&O->trace.count, (size_t)1);
     if (rc != IST_OK) { delete O; return rc; }
@@ -707,8 +868,8 @@ static int lbfgs_create_common(ist_lbfgs** out, ist_plan* plan, int batch, int n
     P.losses = O->losses;
     cudaMemset(P.frames, 0, sizeof(LbFrame) * P.NB);
     cudaMemset(P.dmax_part, 0, sizeof(float) * P.NB * P.nblk);
-    cudaMemset(P.SY, 0, sizeof(double) * P.NB * LB_MAXH * LB_MAXH);
-    cudaMemset(P.YY, 0, sizeof(double) * P.NB * LB_MAXH * LB_MAXH);
+    cudaMemset(P.SY, 0, sizeof(double) * P.NB * LB_MAXH * LB_LDG);
+    cudaMemset(P.YY, 0, sizeof(double) * P.NB * LB_MAXH * LB_LDG);
     cudaMemset(P.d, 0, sizeof(float) * vn);
     cudaMemset(P.prev_g, 0, sizeof(float) * vn);
     cudaMemset(O->trace.count, 0, sizeof(int));

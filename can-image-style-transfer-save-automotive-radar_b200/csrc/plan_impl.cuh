@@ -10,7 +10,9 @@ namespace {
 
 constexpr float kActScale = 0.25f;   // static power-of-two scale of fp16 activation planes (range to 2.6e5, floor 2.4e-7)
 constexpr int kMaxLoss = 15;
-constexpr int kContentBlocks = 64;
+// CTAs of content_partial_kernel per frame: one 256-thread CTA per 2048 elements of relu4_2 at 512^2 (a single load round per
+// thread; 64 CTAs on 148 SMs ran 16 dependent rounds at 0.94 TB/s)
+constexpr int kContentBlocks = 1024;
 
 struct Planes {
     uint16_t* hi = nullptr;
@@ -75,7 +77,7 @@ struct ist_plan {
     // side stream for loss work that does not depend on the deepest layer (runs while the deepest conv, which has too few
     // tiles to fill the GPU, is computed)
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
     ConvWorkspace skw;             // stream-K partial tiles of the conv kernel
     // the first kernel of a closure is launched as programmatically dependent only when the caller knows that the previous
     // operation of the stream is one of this library's kernels (the optimiser loop); see host_common.cuh launch_k
@@ -84,6 +86,8 @@ struct ist_plan {
         skw.release();
         if (ev_fork != nullptr) cudaEventDestroy(ev_fork);
         if (ev_join != nullptr) cudaEventDestroy(ev_join);
+        if (ev_fork2 != nullptr) cudaEventDestroy(ev_fork2);
+        if (ev_join2 != nullptr) cudaEventDestroy(ev_join2);
         if (side != nullptr) cudaStreamDestroy(side);
     }
 };
@@ -363,6 +367,13 @@ int run_loss_finalize(ist_plan* P, float* losses_dev, cudaStream_t st) {
         IST_EW("gram_reduce", rb, st, gram_reduce_kernel<<<grid, 256, 0, st>>>(gp));
         IST_EWK("gram_dmat", db, st, PDL_EW, gram_dmat_kernel, grid, 256, 0, gp);
     }
+    return IST_OK;
+}
+
+// total = sum of the layer losses (python sum(layer_losses), utils.py:32-35). Nothing of the backward pass depends on it, so
+// ist_plan_loss_and_grad runs it on the side stream, off the path between the forward and the backward pass.
+int run_loss_total(ist_plan* P, float* losses_dev, cudaStream_t st, bool pdl) {
+    const int stride = P->n_style + P->n_content + 1;
     LossTotalParams lt;
     memset(&lt, 0, sizeof(lt));
     lt.losses = losses_dev;
@@ -377,7 +388,7 @@ int run_loss_finalize(ist_plan* P, float* losses_dev, cudaStream_t st) {
         lt.c_scale[k] = (float)((double)L.content_w / ((double)L.C * L.H * L.W * kActScale * kActScale));
         lt.n_content++;
     }
-    IST_EWK("loss_total", 64.0 * P->NB, st, PDL_EW, loss_total_kernel, P->NB, 32, 0, lt);
+    IST_EWK("loss_total", 64.0 * P->NB, st, pdl ? PDL_EW : 0, loss_total_kernel, P->NB, 32, 0, lt);
     return IST_OK;
 }
 
@@ -530,6 +541,8 @@ int ist_plan_create(ist_plan** out, int n_layers, const ist_layer_desc* layers, 
     if (rc == IST_OK && cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking) != cudaSuccess) rc = fail(IST_ERR_CUDA, "cudaStreamCreate failed");
     if (rc == IST_OK && cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming) != cudaSuccess) rc = fail(IST_ERR_CUDA, "cudaEventCreate failed");
     if (rc == IST_OK && cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming) != cudaSuccess) rc = fail(IST_ERR_CUDA, "cudaEventCreate failed");
+    if (rc == IST_OK && cudaEventCreateWithFlags(&P->ev_fork2, cudaEventDisableTiming) != cudaSuccess) rc = fail(IST_ERR_CUDA, "cudaEventCreate failed");
+    if (rc == IST_OK && cudaEventCreateWithFlags(&P->ev_join2, cudaEventDisableTiming) != cudaSuccess) rc = fail(IST_ERR_CUDA, "cudaEventCreate failed");
     if (rc != IST_OK) {
         delete P;
         return rc;
@@ -721,9 +734,19 @@ int ist_plan_loss_and_grad(ist_plan* P, const float* x_dev, float* grad_dev, flo
         IST_TRY(run_loss_partials(P, 0, deepest, st));
     }
     IST_TRY(run_loss_finalize(P, losses_dev, st));
+    const bool fork_total = overlap_env && P->side != nullptr;
+    if (fork_total) {
+        IST_CUDA(cudaEventRecord(P->ev_fork2, st));
+        IST_CUDA(cudaStreamWaitEvent(P->side, P->ev_fork2, 0));
+        IST_TRY(run_loss_total(P, losses_dev, P->side, false));      // follows an event wait, not a kernel of its stream
+        IST_CUDA(cudaEventRecord(P->ev_join2, P->side));
+    } else {
+        IST_TRY(run_loss_total(P, losses_dev, st, true));
+    }
     Seeds S;
     S.use_losses = true;
     IST_TRY(run_backward(P, S, deepest, grad_dev, st));
+    if (fork_total) IST_CUDA(cudaStreamWaitEvent(st, P->ev_join2, 0));
     return IST_OK;
 }
 

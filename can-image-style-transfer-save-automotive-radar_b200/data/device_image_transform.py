@@ -63,7 +63,7 @@ class DeviceImageTransform:
             out = torch.empty(b, oh, ow, 3, dtype=torch.uint8, device=self.device)
             tmp = torch.empty(b, h, ow, 3, dtype=torch.uint8, device=self.device) if (oh != h and ow != w) else None
             _lib.check(self.lib.ist_image_resize_u8(_u8ptr(rgb), _u8ptr(out), _u8ptr(tmp) if tmp is not None else None, b, h, w,
-                                                    oh, ow, _lib.stream_ptr()))
+                                                    oh, ow, _lib.stream_ptr(self.device)))
             return out
 
     def prep_u8(self, rgb):
@@ -71,7 +71,7 @@ class DeviceImageTransform:
         with torch.cuda.device(self.device):
             b, h, w, _ = rgb.shape
             x = torch.empty(b, 3, h, w, dtype=torch.float32, device=self.device)
-            _lib.check(self.lib.ist_image_prep_u8(_u8ptr(rgb), _lib.ptr(x), b, h, w, self.mean, _lib.stream_ptr()))
+            _lib.check(self.lib.ist_image_prep_u8(_u8ptr(rgb), _lib.ptr(x), b, h, w, self.mean, _lib.stream_ptr(self.device)))
             return x
 
     def post_u8(self, x):
@@ -83,7 +83,7 @@ class DeviceImageTransform:
         with torch.cuda.device(self.device):
             b, _, h, w = x.shape
             rgb = torch.empty(b, h, w, 3, dtype=torch.uint8, device=self.device)
-            _lib.check(self.lib.ist_image_post_u8(_lib.ptr(x), _u8ptr(rgb), b, h, w, self.mean, _lib.stream_ptr()))
+            _lib.check(self.lib.ist_image_post_u8(_lib.ptr(x), _u8ptr(rgb), b, h, w, self.mean, _lib.stream_ptr(self.device)))
             return rgb
 
     # ---- the reference's two methods ------------------------------------------------------------------------------------
@@ -109,5 +109,5 @@ class DeviceImageTransform:
             work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             x_hi = torch.empty(b, 3, oh, ow, dtype=torch.float32, device=self.device)
             _lib.check(self.lib.ist_image_handoff(_lib.ptr(x_lo), _lib.ptr(x_hi), _u8ptr(work), nbytes, b, h, w, oh, ow, self.mean,
-                                                  _lib.stream_ptr()))
+                                                  _lib.stream_ptr(self.device)))
             return x_hi

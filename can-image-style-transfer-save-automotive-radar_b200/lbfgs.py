@@ -69,7 +69,7 @@ class DeviceLBFGS:
 
     def reset(self):
         """Forget all optimiser state (equivalent to constructing a new optim.LBFGS([x])); keeps buffers and the captured graph."""
-        _lib.check(self.lib.ist_lbfgs_reset(self.h, _lib.stream_ptr()))
+        _lib.check(self.lib.ist_lbfgs_reset(self.h, _lib.stream_ptr(self.device)))
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
@@ -93,7 +93,7 @@ class DeviceLBFGS:
         evals = ctypes.c_int(0)
         loss = ctypes.c_float(0.0)
         _lib.check(self.lib.ist_lbfgs_step(self.h, ctypes.c_void_p(x.data_ptr()), ctypes.byref(evals), ctypes.byref(loss),
-                                           _lib.stream_ptr()))
+                                           _lib.stream_ptr(self.device)))
         return evals.value, loss.value
 
     def last_losses(self):

@@ -18,10 +18,11 @@ from PIL import Image
 
 from .config import get_cfg_defaults
 from .model import build_model
-from .model.engine import do_transfer_style, do_transfer_style_batch
+from .model.engine import do_transfer_style
 from .model.engine.hr_transfer_style import do_hr_transfer_style
 from .model.meta_arch import GramMSELoss, StyleTransfer
-from .parallel import gather_frames, init_distributed, shard_indices
+from .parallel import gather_results, init_distributed, shard_indices
+from .pipeline import FramePipeline
 from .util.logger import setup_logger
 
 
@@ -82,12 +83,17 @@ def main(argv=None):
     parser.add_argument("--style-img", default="", help="the shared style (lidar) image")
     parser.add_argument("--output-dir", default="./output/full_transfer/", help="where the stylised frames go")
     parser.add_argument("--max-frames", type=int, default=0, help="process at most this many frames (0 = all)")
-    parser.add_argument("--high-resolution", action="store_true", help="run the coarse-to-fine second stage")
+    parser.add_argument("--high-resolution", action="store_true", help="run the coarse-to-fine second stage (serial per frame)")
     parser.add_argument("--frames-per-batch", type=int, default=1,
                         help="optimise this many (independent, equally sized) frames side by side on each GPU")
+    parser.add_argument("--prefetch", type=int, default=2, help="batches decoded and uploaded ahead of the GPU")
+    parser.add_argument("--skip-existing", action="store_true", help="do not recompute frames whose output file exists")
+    parser.add_argument("--no-gather", action="store_true", help="skip the end-of-run gather of the finished frames (files only)")
+    parser.add_argument("--summary-json", default="", help="rank 0 writes a one-line JSON summary (frames/s incl. I/O) here")
     parser.add_argument("opts", help="Modify config options using the command-line", default=None, nargs=argparse.REMAINDER)
     args = parser.parse_args(argv)
 
+    t_all = time.time()
     cfg = get_cfg_defaults()
     if args.config_file:
         cfg.merge_from_file(args.config_file)
@@ -103,36 +109,60 @@ def main(argv=None):
     logger.info(args)
 
     model, device = get_model(cfg)
+    torch.cuda.set_device(device)
     style_image = Image.open(args.style_img or cfg.DATA.STYLE_IMG_PATH).convert('RGB')      # one shared style, main.py:184-185
     frames = sorted(glob.glob(os.path.join(args.content_dir, "*.png"))) if args.content_dir else [cfg.DATA.CONTENT_IMG_PATH]
     if args.max_frames > 0:
         frames = frames[: args.max_frames]
     mine = shard_indices(len(frames), rank, world)
-    t_all = time.time()
-    results = []
-    fpb = max(1, args.frames_per_batch)
-    for b0 in range(0, len(mine), fpb):
-        group = mine[b0:b0 + fpb]
-        start = time.time()
-        contents = [Image.open(frames[i]).convert('RGB') for i in group]
-        if len(group) == 1:
-            outs = [do_transfer_style(cfg, model, contents[0], style_image, device)]
-        else:
-            outs = do_transfer_style_batch(cfg, model, contents, style_image, device)
-        for i, content_image, out_image in zip(group, contents, outs):
-            if args.high_resolution:
-                out_image = do_hr_transfer_style(cfg, model, content_image, style_image, out_image, device)
-            out_image.save(os.path.join(cfg.OUTPUT.DIR, os.path.basename(frames[i])))
-            results.append(torch.from_numpy(np.asarray(out_image).copy()))
-        logger.info("frames %s: %f second per frame" % ([os.path.basename(frames[i]) for i in group], (time.time() - start) / len(group)))
-    if world > 1 and results:
-        local = torch.stack(results).to(device)
-        gathered = gather_frames(local, len(frames), rank, world)
+
+    if args.high_resolution:
+        # the coarse-to-fine second stage re-reads the content image at HRDATA.IMG_SIZE: plain per-frame loop (main.py:59-75)
+        done = []
+        for i in mine:
+            out_path = os.path.join(cfg.OUTPUT.DIR, os.path.splitext(os.path.basename(frames[i]))[0] + ".png")
+            if args.skip_existing and os.path.exists(out_path):
+                continue
+            content_image = Image.open(frames[i]).convert('RGB')
+            out_image, x = do_transfer_style(cfg, model, content_image, style_image, device, return_tensor=True, save=False)
+            out_image = do_hr_transfer_style(cfg, model, content_image, style_image, x, device, save=False)
+            out_image.save(out_path)
+            done.append(i)
+        results, stats = {}, {"frames": len(done), "skipped": len(mine) - len(done)}
+    else:
+        pipe = FramePipeline(cfg, model, device, style_image, cfg.OUTPUT.DIR, frames_per_batch=args.frames_per_batch,
+                             prefetch=args.prefetch, keep_results=(world > 1 and not args.no_gather) or bool(args.summary_json))
+        done = pipe.run(frames, mine, skip_existing=args.skip_existing)
+        pipe.close()
+        results, stats = pipe.results, dict(pipe.stats)
+    logger.info("rank %d: %d frames done, %d skipped (%s)" % (rank, len(done), stats.get("skipped", 0),
+                                                             ", ".join("%s=%.3g" % kv for kv in sorted(stats.items()))))
+
+    # every rank enters the collectives, also with an empty shard (n_frames < world) or mixed frame sizes
+    gathered = None
+    if not args.no_gather and not args.high_resolution:
+        gathered = gather_results(results, len(frames), rank, world, device)
         if rank == 0:
-            logger.info("gathered %d frames of shape %s on rank 0" % (gathered.shape[0], tuple(gathered.shape[1:])))
+            logger.info("gathered %s" % ("%d frames of shape %s on rank 0" % (gathered.shape[0], tuple(gathered.shape[1:]))
+                                          if gathered is not None else "nothing (frames differ in size or were skipped: the files are the result)"))
+    torch.cuda.synchronize(device)
+    if world > 1:
+        torch.distributed.barrier()
+    wall = time.time() - t_all
     if rank == 0:
-        n = max(1, len(mine))
-        logger.info("avg time per frame on this rank: %f" % ((time.time() - t_all) / n))
+        n = sum(1 for _ in frames)
+        logger.info("avg time per frame: %f (%d frames on %d GPU(s), %.2f frames/s incl. model load, style target, I/O and gather)"
+                    % (wall / max(1, n), n, world, n / wall))
+        if args.summary_json:
+            import hashlib
+            import json
+            digest = hashlib.sha256(gathered.cpu().numpy().tobytes()).hexdigest() if gathered is not None else None
+            with open(args.summary_json, "w") as f:
+                f.write(json.dumps({"frames": n, "n_gpus": world, "wall_s": wall, "frames_per_s": n / wall,
+                                    "frames_per_batch": args.frames_per_batch, "gathered_sha256": digest,
+                                    "rank0_stats": {k: float(v) for k, v in stats.items()}}) + "\n")
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

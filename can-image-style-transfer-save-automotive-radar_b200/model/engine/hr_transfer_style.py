@@ -16,7 +16,7 @@ from .utils import transform_image, optimize
 logger = setup_logger('style-transfer', False)
 
 
-def do_hr_transfer_style(cfg, model, content_image, style_image, optimized_image, device, return_tensor=False):
+def do_hr_transfer_style(cfg, model, content_image, style_image, optimized_image, device, return_tensor=False, save=True):
     logger.info("Start transferring to high resolution.")
     image_transformer = DeviceImageTransform(cfg.HRDATA.IMG_SIZE, cfg.DATA.IMAGENET_MEAN, device)
 
@@ -32,8 +32,9 @@ def do_hr_transfer_style(cfg, model, content_image, style_image, optimized_image
     optimized_image = optimize(model, content_image, style_image, optimized_image, cfg, cfg.HRLOSS.MAX_ITER)
 
     out_image = image_transformer.post_preparation(optimized_image.data[0])
-    os.makedirs(cfg.OUTPUT.DIR, exist_ok=True)
-    out_image.save(cfg.OUTPUT.DIR + cfg.OUTPUT.HR_FILE_NAME)
+    if save:
+        os.makedirs(cfg.OUTPUT.DIR, exist_ok=True)
+        out_image.save(cfg.OUTPUT.DIR + cfg.OUTPUT.HR_FILE_NAME)
     if return_tensor:
         return out_image, optimized_image.data
     return out_image

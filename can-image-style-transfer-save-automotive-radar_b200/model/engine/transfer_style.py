@@ -15,7 +15,7 @@ logger = setup_logger('style-transfer', False)
 
 
 def do_transfer_style(cfg, model, content_image, style_image, device, content_only=False, style_only=False, opt='LBFGS',
-                      saliency_map=False, return_tensor=False):
+                      saliency_map=False, return_tensor=False, save=True):
     """`return_tensor=True` (not in the reference) also returns the optimised float32 [1,3,h,w] device tensor, which
     `do_hr_transfer_style` accepts in place of the PIL image to keep the coarse-to-fine hand-off on the device."""
     logger.info("Start transferring.")
@@ -32,8 +32,9 @@ def do_transfer_style(cfg, model, content_image, style_image, device, content_on
                                    content_only, style_only, opt)
 
     out_image = image_transformer.post_preparation(optimized_image.data[0])
-    os.makedirs(cfg.OUTPUT.DIR, exist_ok=True)
-    out_image.save(cfg.OUTPUT.DIR + cfg.OUTPUT.FILE_NAME)
+    if save:      # transfer_style.py:43 writes OUTPUT.DIR + FILE_NAME for every frame; batch drivers with several ranks pass save=False
+        os.makedirs(cfg.OUTPUT.DIR, exist_ok=True)
+        out_image.save(cfg.OUTPUT.DIR + cfg.OUTPUT.FILE_NAME)
     if return_tensor:
         return out_image, optimized_image.data
     return out_image

@@ -13,7 +13,8 @@ class _GramFn(torch.autograd.Function):
         b, c, h, w = x.shape
         lib = _lib.load()
         g = torch.empty(b, c, c, device=x.device, dtype=torch.float32)
-        _lib.check(lib.ist_op_gram(_lib.ptr(x), _lib.ptr(g), b, c, h, w, _lib.stream_ptr()))
+        with torch.cuda.device(x.device):          # the per-op entry points work on the current device
+            _lib.check(lib.ist_op_gram(_lib.ptr(x), _lib.ptr(g), b, c, h, w, _lib.stream_ptr(x.device)))
         ctx.save_for_backward(x)
         return g
 
@@ -22,8 +23,9 @@ class _GramFn(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         b, c, h, w = x.shape
         dx = torch.empty_like(x)
-        _lib.check(_lib.load().ist_op_gram_bwd(_lib.ptr(x), _lib.ptr(dg.contiguous().float()), _lib.ptr(dx), b, c, h, w,
-                                               _lib.stream_ptr()))
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().ist_op_gram_bwd(_lib.ptr(x), _lib.ptr(dg.contiguous().float()), _lib.ptr(dx), b, c, h, w,
+                                                   _lib.stream_ptr(x.device)))
         return dx
 
 

@@ -16,8 +16,9 @@ class _GramMSEFn(torch.autograd.Function):
         t = target.detach().contiguous().float().view(c, c)
         loss = torch.empty(b, device=x.device, dtype=torch.float32)
         dx = torch.empty_like(x)
-        _lib.check(_lib.load().ist_op_gram_mse(_lib.ptr(x), _lib.ptr(t), 1.0, _lib.ptr(loss), _lib.ptr(dx), b, c, h, w,
-                                               _lib.stream_ptr()))
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().ist_op_gram_mse(_lib.ptr(x), _lib.ptr(t), 1.0, _lib.ptr(loss), _lib.ptr(dx), b, c, h, w,
+                                                   _lib.stream_ptr(x.device)))
         ctx.save_for_backward(dx)
         return loss[0]
 

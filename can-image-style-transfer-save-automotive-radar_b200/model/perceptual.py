@@ -87,8 +87,9 @@ class _BatchMSE(torch.autograd.Function):
         b, c, h, w = x.shape
         per_frame = torch.empty(b, 2, device=x.device, dtype=torch.float32)
         dx = torch.empty_like(x)
-        _lib.check(_lib.load().ist_op_mse(_lib.ptr(x), _lib.ptr(t), 1.0 / b, _lib.ptr(per_frame), _lib.ptr(dx), b, c, h, w,
-                                          _lib.stream_ptr()))
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().ist_op_mse(_lib.ptr(x), _lib.ptr(t), 1.0 / b, _lib.ptr(per_frame), _lib.ptr(dx), b, c, h, w,
+                                              _lib.stream_ptr(x.device)))
         ctx.save_for_backward(dx)
         return per_frame[:, 0].sum()
 

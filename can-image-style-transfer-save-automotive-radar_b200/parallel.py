@@ -52,6 +52,36 @@ def gather_frames(local, n_frames, rank, world):
     return out[idx % world, idx // world]
 
 
+def gather_results(results, n_frames, rank, world, device):
+    """End-of-run gather of finished frames for the batch driver. `results`: {frame index: tensor [H,W,3]} of this rank
+    (possibly empty). EVERY rank must call this (ranks with an empty shard included): the ranks first agree, through one
+    all_reduce, on whether all frames have one common shape; only then the fixed-shape all_gather runs. Returns the
+    [n_frames,H,W,3] batch in frame order, or None when the frames differ in shape (Scale keeps the aspect ratio, so a
+    directory may mix sizes) or some frame is missing (skip-existing) — the per-frame files are the result in that case."""
+    if world == 1:
+        if len(results) != n_frames or len({tuple(t.shape) for t in results.values()}) != 1:
+            return None
+        return torch.stack([results[i] for i in range(n_frames)])
+    big = 1 << 30
+    hs = [int(t.shape[0]) for t in results.values()]
+    ws = [int(t.shape[1]) for t in results.values()]
+    lo = torch.tensor([min(hs) if hs else big, min(ws) if ws else big], dtype=torch.int64, device=device)
+    hi = torch.tensor([max(hs) if hs else 0, max(ws) if ws else 0], dtype=torch.int64, device=device)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    cnt = torch.tensor([len(results)], dtype=torch.int64, device=device)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    if int(cnt) != n_frames or int(lo[0]) != int(hi[0]) or int(lo[1]) != int(hi[1]) or int(hi[0]) == 0:
+        return None
+    mine = shard_indices(n_frames, rank, world)
+    if sorted(results.keys()) != mine:
+        raise ValueError("gather_results expects the round-robin shard of this rank")
+    h, w = int(hi[0]), int(hi[1])
+    dtype = next(iter(results.values())).dtype if results else torch.uint8
+    local = torch.stack([results[i] for i in mine]) if mine else torch.zeros((0, h, w, 3), dtype=dtype, device=device)
+    return gather_frames(local.to(device), n_frames, rank, world)
+
+
 def max_over_ranks(value, device):
     """Max of a python float over ranks (for device-timed numbers, which are reported as the slowest rank)."""
     if not dist.is_initialized():

@@ -70,7 +70,7 @@ class Plan:
         for ci, name in enumerate(self.conv_names):
             w = state[name + ".weight"].detach().to(self.device, torch.float32).contiguous()
             b = state[name + ".bias"].detach().to(self.device, torch.float32).contiguous()
-            _lib.check(self.lib.ist_plan_set_weights(self.h, ci, _lib.ptr(w), _lib.ptr(b), _lib.stream_ptr()))
+            _lib.check(self.lib.ist_plan_set_weights(self.h, ci, _lib.ptr(w), _lib.ptr(b), _lib.stream_ptr(self.device)))
 
     # ---- forward / features -------------------------------------------------------------------------------------------------
     def _check_x(self, x):
@@ -79,7 +79,7 @@ class Plan:
 
     def forward(self, x, upto_key):
         self._check_x(x)
-        _lib.check(self.lib.ist_plan_forward(self.h, _lib.ptr(x), self.out_index[upto_key], _lib.stream_ptr()))
+        _lib.check(self.lib.ist_plan_forward(self.h, _lib.ptr(x), self.out_index[upto_key], _lib.stream_ptr(self.device)))
 
     def feature_shape(self, key):
         c, h, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
@@ -89,7 +89,7 @@ class Plan:
     def feature(self, key):
         c, h, w = self.feature_shape(key)
         out = torch.empty(self.batch, c, h, w, device=self.device, dtype=torch.float32)
-        _lib.check(self.lib.ist_plan_get_feature(self.h, self.out_index[key], _lib.ptr(out), _lib.stream_ptr()))
+        _lib.check(self.lib.ist_plan_get_feature(self.h, self.out_index[key], _lib.ptr(out), _lib.stream_ptr(self.device)))
         return out
 
     def pool_index(self, key):
@@ -97,7 +97,7 @@ class Plan:
         forward (first maximum in row-major order), 4 where the pooled value is not positive."""
         c, h, w = self.feature_shape(key)
         out = torch.empty(self.batch, c, h, w, device=self.device, dtype=torch.uint8)
-        _lib.check(self.lib.ist_plan_get_pool_index(self.h, self.out_index[key], _lib.ptr(out, torch.uint8), _lib.stream_ptr()))
+        _lib.check(self.lib.ist_plan_get_pool_index(self.h, self.out_index[key], _lib.ptr(out, torch.uint8), _lib.stream_ptr(self.device)))
         return out
 
     def masks(self, upto_key):
@@ -114,7 +114,7 @@ class Plan:
     def gram(self, key):
         c, _, _ = self.feature_shape(key)
         out = torch.empty(self.batch, c, c, device=self.device, dtype=torch.float32)
-        _lib.check(self.lib.ist_plan_gram(self.h, self.out_index[key], _lib.ptr(out), _lib.stream_ptr()))
+        _lib.check(self.lib.ist_plan_gram(self.h, self.out_index[key], _lib.ptr(out), _lib.stream_ptr(self.device)))
         return out
 
     # ---- losses -----------------------------------------------------------------------------------------------------------------
@@ -131,10 +131,10 @@ class Plan:
     def set_style_target(self, slot, gram):
         g = gram.detach().to(self.device, torch.float32).contiguous()
         g = g[0] if g.dim() == 3 else g
-        _lib.check(self.lib.ist_plan_set_style_target(self.h, slot, _lib.ptr(g.contiguous()), _lib.stream_ptr()))
+        _lib.check(self.lib.ist_plan_set_style_target(self.h, slot, _lib.ptr(g.contiguous()), _lib.stream_ptr(self.device)))
 
     def capture_content_target(self, slot):
-        _lib.check(self.lib.ist_plan_capture_content_target(self.h, slot, _lib.stream_ptr()))
+        _lib.check(self.lib.ist_plan_capture_content_target(self.h, slot, _lib.stream_ptr(self.device)))
 
     def loss_and_grad(self, x, grad=None, losses=None):
         """closure body (utils.py:29-41): returns (losses [batch, n+1], grad [batch,3,H,W]); last loss column = total."""
@@ -143,7 +143,7 @@ class Plan:
             grad = torch.empty_like(x)
         if losses is None:
             losses = torch.empty(self.batch, self.n_style + self.n_content + 1, device=self.device, dtype=torch.float32)
-        _lib.check(self.lib.ist_plan_loss_and_grad(self.h, _lib.ptr(x), _lib.ptr(grad), _lib.ptr(losses), _lib.stream_ptr()))
+        _lib.check(self.lib.ist_plan_loss_and_grad(self.h, _lib.ptr(x), _lib.ptr(grad), _lib.ptr(losses), _lib.stream_ptr(self.device)))
         return losses, grad
 
     def backward(self, seeds):
@@ -153,5 +153,5 @@ class Plan:
         idx = (ctypes.c_int * len(keys))(*[self.out_index[k] for k in keys])
         ptrs = (ctypes.c_void_p * len(keys))(*[t.data_ptr() for t in ts])
         grad = torch.empty(self.batch, 3, self.H, self.W, device=self.device, dtype=torch.float32)
-        _lib.check(self.lib.ist_plan_backward(self.h, len(keys), idx, ptrs, _lib.ptr(grad), _lib.stream_ptr()))
+        _lib.check(self.lib.ist_plan_backward(self.h, len(keys), idx, ptrs, _lib.ptr(grad), _lib.stream_ptr(self.device)))
         return grad

@@ -83,6 +83,14 @@ def expanded(dot):
                 for j in range(h):
                     acc = acc + torch.tensor(-H*al[j],dtype=torch.float32)*Y[j] + torch.tensor(c[j],dtype=torch.float32)*S[j]
                 d = acc.double()
+            elif MODE=='f32_c2':     # fp32 accumulation, every coefficient as an fp32 hi + lo pair
+                def two(v):
+                    hi=torch.tensor(v,dtype=torch.float32); lo=torch.tensor(v-float(hi),dtype=torch.float32); return hi,lo
+                h0,l0=two(-H); acc = h0*g; acc = acc + l0*g
+                for j in range(h):
+                    a1,a2=two(-H*al[j]); b1,b2=two(c[j])
+                    acc = acc + a1*Y[j]; acc = acc + a2*Y[j]; acc = acc + b1*S[j]; acc = acc + b2*S[j]
+                d = acc.double()
             elif MODE=='f64':
                 acc = -H*g.double()
                 for j in range(h):
@@ -118,7 +126,13 @@ class DTile:
     def mat(self,A,B): return torch.stack([self._t(A[i][None,:]*B) for i in range(A.shape[0])]).numpy()
     def mv(self,A,g): return self._t(A*g[None,:]).numpy()
 import itertools
-for (name,dd),MODE in itertools.product((('exact fp64 dots of fp32 history',D64()),('fp32 in-tile dots',DTile())),('f32','f64','f32coef64','kahan')):
+class DLane16(DTile):
+    # fp32 sums over the 16 elements one lane holds, float64 from there on (shuffle tree and across tiles in double)
+    def _t(self,P):
+        n=P.shape[-1]; pad=(-n)%16
+        if pad: P=torch.nn.functional.pad(P,(0,pad))
+        return P.view(*P.shape[:-1],-1,16).sum(-1,dtype=torch.float32).double().sum(-1)
+for (name,dd),MODE in itertools.product((('exact fp64 dots of fp32 history',D64()),('fp32 in-tile dots',DTile()),('fp32 per-lane (16 elements) dots',DLane16())),('f32','f64','f32_c2')):
     out = expanded(dd); name=name+' / d accumulation '+MODE
     errs=[float((a-b['d']).norm()/b['d'].norm()) for a,b in zip(out,log64)]
     print(name,'worst',max(errs),'at',int(np.argmax(errs)), 'median', float(np.median(errs)))
