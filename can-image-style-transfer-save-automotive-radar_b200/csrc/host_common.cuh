@@ -579,6 +579,16 @@ inline void gram_split_plan(int NB, int HW, int C, int* splits, int* chunks_per_
     if (want < 1) want = 1;
     if (want > total_chunks) want = total_chunks;
     if (want > 160) want = 160;
+    // ... but a split of very few 64-pixel chunks costs more than it gives: every split writes a full C x C fp32 partial that
+    // gram_reduce_kernel reads back (relu4_1 / relu5_1: 15 splits x 1 MB each for 1-4 chunks of tensor work). At least
+    // `min_chunks` chunks per split (IST_B200_GRAM_MIN_CHUNKS overrides).
+    static int min_chunks = 0;
+    if (min_chunks == 0) {
+        const char* e = getenv("IST_B200_GRAM_MIN_CHUNKS");
+        min_chunks = (e != nullptr && atoi(e) > 0) ? atoi(e) : 1;
+    }
+    if (want > (total_chunks + min_chunks - 1) / min_chunks) want = (total_chunks + min_chunks - 1) / min_chunks;
+    if (want < 1) want = 1;
     const int cps = (total_chunks + want - 1) / want;
     *chunks_per_split = cps;
     *splits = (total_chunks + cps - 1) / cps;

@@ -115,6 +115,35 @@ __device__ __forceinline__ void lb_store16(float* __restrict__ p, size_t base, i
     }
 }
 
+// 8 elements per lane of a 256-element warp tile (update pass): element (k, lane, j) = base + k*128 + lane*4 + j
+constexpr int LB_UT = 256;
+__device__ __forceinline__ void lb_load8(const float* __restrict__ p, size_t base, int n_left, int lane, bool vec, float (&v)[8]) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int off = k * 128 + lane * 4;
+        if (vec && off + 3 < n_left) {
+            const float4 t = *reinterpret_cast<const float4*>(p + base + off);
+            v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[4 * k + j] = (off + j < n_left) ? p[base + off + j] : 0.f;
+        }
+    }
+}
+__device__ __forceinline__ void lb_store8(float* __restrict__ p, size_t base, int n_left, int lane, bool vec, const float (&v)[8]) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int off = k * 128 + lane * 4;
+        if (vec && off + 3 < n_left) {
+            *reinterpret_cast<float4*>(p + base + off) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (off + j < n_left) p[base + off + j] = v[4 * k + j];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // pass 1: all dot products of this iteration. grid (nblk_dots, NB), 12 warps; each warp owns whole warp-tiles, so there
 // is no block-level synchronisation inside the history loop.
@@ -598,7 +627,7 @@ __device__ __forceinline__ void lb_split(double c, float& h, float& l) {
     l = (float)(c - (double)h);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 lbfgs_update_kernel(const LbParams P) {
     __shared__ float wmax[8];
     __shared__ int s_slot[LB_MAXH];
@@ -622,63 +651,64 @@ lbfgs_update_kernel(const LbParams P) {
         const bool vec = ((n & 3) == 0);
         const bool has_prev = F.n_iter >= 2;      // a previous direction exists (n_iter was already incremented)
         const float t_old_new = F.t_f;
-        const int ntiles = (n + LB_WT - 1) / LB_WT;
+        const int ntiles = (n + LB_UT - 1) / LB_UT;      // 256-element warp tiles: twice the warps of a 512-element tiling,
+                                                         // half the registers per thread — the compensated sum is latency-bound otherwise
         float cgh, cgl, cynh, cynl, csnh, csnl;
         lb_split(F.cg_d, cgh, cgl);
         lb_split(F.cy_new, cynh, cynl);
         lb_split(F.cs_new, csnh, csnl);
         const int nread = F.nread, accepted = F.accepted, new_slot = F.new_slot, apply = F.apply;
         for (int tile = blockIdx.x * 8 + warp; tile < ntiles; tile += gridDim.x * 8) {
-            const size_t base = (size_t)tile * LB_WT;
+            const size_t base = (size_t)tile * LB_UT;
             const int n_left = n - (int)base;
-            float gv[16], hi[16], lo[16];
-            lb_load16(P.g + fo, base, n_left, lane, vec, gv);
+            float gv[8], hi[8], lo[8];
+            lb_load8(P.g + fo, base, n_left, lane, vec, gv);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) { hi[e] = 0.f; lo[e] = 0.f; lb_dot2_step(hi[e], lo[e], cgh, cgl, gv[e]); }
+            for (int e = 0; e < 8; ++e) { hi[e] = 0.f; lo[e] = 0.f; lb_dot2_step(hi[e], lo[e], cgh, cgl, gv[e]); }
             if (has_prev) {
-                float yv[16], sv[16];
-                lb_load16(P.prev_g + fo, base, n_left, lane, vec, yv);
-                lb_load16(P.d + fo, base, n_left, lane, vec, sv);
+                float yv[8], sv[8];
+                lb_load8(P.prev_g + fo, base, n_left, lane, vec, yv);
+                lb_load8(P.d + fo, base, n_left, lane, vec, sv);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) { yv[e] = gv[e] - yv[e]; }
+                for (int e = 0; e < 8; ++e) { yv[e] = gv[e] - yv[e]; }
                 if (accepted) {
                     // s_new = t_prev * d_old (lbfgs.py:404): t_prev is the step size saved by lbfgs_reduce_kernel before the
                     // solve replaced F.t with the step size of the new direction
                     const float tp = F.t_prev_f;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
+                    for (int e = 0; e < 8; ++e) {
                         sv[e] = tp * sv[e];
                         lb_dot2_step(hi[e], lo[e], csnh, csnl, sv[e]);
                         lb_dot2_step(hi[e], lo[e], cynh, cynl, yv[e]);
                     }
                     const size_t ho = ((size_t)new_slot * P.NB + b) * (size_t)n;
-                    lb_store16(P.S + ho, base, n_left, lane, vec, sv);
-                    lb_store16(P.Y + ho, base, n_left, lane, vec, yv);
+                    lb_store8(P.S + ho, base, n_left, lane, vec, sv);
+                    lb_store8(P.Y + ho, base, n_left, lane, vec, yv);
                 }
             }
             for (int i = 0; i < nread; ++i) {
                 const size_t ho = ((size_t)s_slot[i] * P.NB + b) * (size_t)n;
-                float s_i[16], y_i[16];
-                lb_load16(P.S + ho, base, n_left, lane, vec, s_i);
-                lb_load16(P.Y + ho, base, n_left, lane, vec, y_i);
+                float s_i[8], y_i[8];
+                lb_load8(P.S + ho, base, n_left, lane, vec, s_i);
+                lb_load8(P.Y + ho, base, n_left, lane, vec, y_i);
                 const float cyh = s_cyh[i], cyl = s_cyl[i], csh = s_csh[i], csl = s_csl[i];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
+                for (int e = 0; e < 8; ++e) {
                     lb_dot2_step(hi[e], lo[e], csh, csl, s_i[e]);
                     lb_dot2_step(hi[e], lo[e], cyh, cyl, y_i[e]);
                 }
             }
-            float dv[16];
+            float dv[8];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) { dv[e] = __fadd_rn(hi[e], lo[e]); dmax = fmaxf(dmax, fabsf(dv[e])); }
-            lb_store16(P.d + fo, base, n_left, lane, vec, dv);
-            lb_store16(P.prev_g + fo, base, n_left, lane, vec, gv);
+            for (int e = 0; e < 8; ++e) { dv[e] = __fadd_rn(hi[e], lo[e]); dmax = fmaxf(dmax, fabsf(dv[e])); }
+            lb_store8(P.d + fo, base, n_left, lane, vec, dv);
+            lb_store8(P.prev_g + fo, base, n_left, lane, vec, gv);
             if (apply) {
-                float xv[16];
-                lb_load16(P.x + fo, base, n_left, lane, vec, xv);
+                float xv[8];
+                lb_load8(P.x + fo, base, n_left, lane, vec, xv);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) xv[e] = fmaf(t_old_new, dv[e], xv[e]);
-                lb_store16(P.x + fo, base, n_left, lane, vec, xv);
+                for (int e = 0; e < 8; ++e) xv[e] = fmaf(t_old_new, dv[e], xv[e]);
+                lb_store8(P.x + fo, base, n_left, lane, vec, xv);
             }
         }
     }
@@ -833,8 +863,9 @@ static int lbfgs_create_common(ist_lbfgs** out, ist_plan* plan, int batch, int n
     P.n = n;
     P.m = history_size;
     const int ntiles = (P.n + LB_WT - 1) / LB_WT;
-    int nblk = (ntiles + 7) / 8;
-    if (nblk > 2 * num_sms()) nblk = 2 * num_sms();
+    const int utiles = (P.n + LB_UT - 1) / LB_UT;
+    int nblk = (utiles + 7) / 8;
+    if (nblk > 4 * num_sms()) nblk = 4 * num_sms();
     if (nblk < 1) nblk = 1;
     P.nblk = nblk;
     int nblk_dots = (ntiles + LB_DOTS_WARPS - 1) / LB_DOTS_WARPS;        // one CTA per SM (its ring takes the shared memory)

@@ -109,6 +109,8 @@ def main(argv=None):
     logger.info(args)
 
     model, device = get_model(cfg)
+    if device.type == 'cuda' and device.index is None:      # MODEL.DEVICE = 'cuda' (defaults.py:14): the current device
+        device = torch.device('cuda', torch.cuda.current_device())
     torch.cuda.set_device(device)
     style_image = Image.open(args.style_img or cfg.DATA.STYLE_IMG_PATH).convert('RGB')      # one shared style, main.py:184-185
     frames = sorted(glob.glob(os.path.join(args.content_dir, "*.png"))) if args.content_dir else [cfg.DATA.CONTENT_IMG_PATH]

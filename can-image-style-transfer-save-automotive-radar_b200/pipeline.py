@@ -34,6 +34,8 @@ class FramePipeline:
                  keep_results=False, max_iterations=None):
         self.cfg, self.model = cfg, model
         self.device = torch.device(device)
+        if self.device.type == 'cuda' and self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
         self.output_dir = output_dir
         self.fpb = max(1, int(frames_per_batch))
         self.depth = max(1, int(prefetch)) * self.fpb
