@@ -35,7 +35,13 @@ struct HaloCfg {
     static constexpr int B_ROWS = PAIR ? N_TILE / 2 : N_TILE;      // weight rows this CTA holds per tap
     static constexpr int B_PLANE = B_ROWS * 128;
     static constexpr int B_STAGE = 2 * B_PLANE;
-    static constexpr int B_STAGES = PAIR ? ((N_TILE == 128) ? 4 : 8) : ((N_TILE == 128) ? 3 : 4);
+#ifndef IST_B_STAGES_N64_PAIR
+#define IST_B_STAGES_N64_PAIR 12
+#endif
+    // pair / N = 64: 12 x 8 KB weight stages (a tile of the 64 -> 64 layers is 9 taps: the ring then spans a tile boundary, and
+    // the issuers' largest wait, B-full at 16 % of the launch with 8 stages, shrinks); the shared memory is there (222 KB in all)
+    static constexpr int B_STAGES = PAIR ? ((N_TILE == 128) ? 4 : IST_B_STAGES_N64_PAIR) : ((N_TILE == 128) ? 3 : 4);
+    static_assert(B_STAGES <= 12, "barrier block holds 12 weight-stage barrier pairs");
     // tensor-memory accumulators (N_TILE fp32 columns each, 512 columns in all):
     //   N_TILE = 128: [main 0][main 1][main 2 | Gram][cross]      (third main buffer when no Gram k-steps are fused)
     //   N_TILE =  64: [main 0..3][cross 0][cross 1][Gram 0][Gram 1]   (the Gram accumulator follows the cross buffer's parity)
@@ -150,19 +156,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t b_base = smem_base + Cfg::A_STAGES * Cfg::A_STAGE;
     const uint32_t o_base = b_base + Cfg::B_STAGES * Cfg::B_STAGE;      // output staging (1024-aligned planes)
     const uint32_t bar_base = o_base + Cfg::OUT_BUFS * Cfg::OUT_BYTES;
-    // barriers (8 B each): a_full[3] @0, a_empty[3] @24, b_full[8] @48, b_empty[8] @112, main_full[4] @176,
-    // main_empty[4] @208, cross_full[2] @240, cross_empty[2] @256, tmem base address @272
+    // barriers (8 B each): a_full[3] @0, a_empty[3] @24, b_full[12] @48, b_empty[12] @144, main_full[4] @240,
+    // main_empty[4] @272, cross_full[2] @304, cross_empty[2] @320, tmem base address @336
     auto afull = [&](int s) { return bar_base + 8u * s; };
     auto aempty = [&](int s) { return bar_base + 24u + 8u * s; };
     auto bfull = [&](int s) { return bar_base + 48u + 8u * s; };
-    auto bempty = [&](int s) { return bar_base + 112u + 8u * s; };
-    auto mfull = [&](uint32_t b) { return bar_base + 176u + 8u * b; };
-    auto mempty = [&](uint32_t b) { return bar_base + 208u + 8u * b; };
-    auto xfull = [&](uint32_t a) { return bar_base + 240u + 8u * a; };
-    auto xempty = [&](uint32_t a) { return bar_base + 256u + 8u * a; };
-    const uint32_t tmem_slot = bar_base + 272u;
+    auto bempty = [&](int s) { return bar_base + 144u + 8u * s; };
+    auto mfull = [&](uint32_t b) { return bar_base + 240u + 8u * b; };
+    auto mempty = [&](uint32_t b) { return bar_base + 272u + 8u * b; };
+    auto xfull = [&](uint32_t a) { return bar_base + 304u + 8u * a; };
+    auto xempty = [&](uint32_t a) { return bar_base + 320u + 8u * a; };
+    const uint32_t tmem_slot = bar_base + 336u;
     volatile uint32_t* tmem_slot_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 272);
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 336);
     // CTA pair: rank 0 leads (issues the MMAs, owns the operand-full and accumulator-empty barriers both CTAs signal)
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     // barrier operations that differ between the two modes

@@ -293,17 +293,52 @@ struct GramFuse {
 template <int N_TILE, bool PAIR>
 inline int launch_halo_t(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                          const CUtensorMap& b_lo, const CUtensorMap& o_hi, const CUtensorMap& o_lo, const CUtensorMap& f_hi,
-                         const CUtensorMap& f_lo, const CUtensorMap& d_hi, const CUtensorMap& d_lo, const ConvParams& p) {
+                         const CUtensorMap& f_lo, const CUtensorMap& d_hi, const CUtensorMap& d_lo, const ConvParams& p_in) {
     static DeviceOnce attr_once;
     if (attr_once.first()) {
         IST_CUDA(cudaFuncSetAttribute(conv_halo_kernel<N_TILE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       HaloCfg<N_TILE, PAIR>::SMEM_BYTES));
     }
-    const int total = p.NB * p.tiles_x * p.tiles_y * p.tiles_n;
-    int groups = conv_workers() / p.sk_cpf;            // frame groups that fit side by side
-    if (groups > p.NB) groups = p.NB;
-    if (groups < 1) groups = 1;
-    const int grid = groups * p.sk_cpf * (PAIR ? 2 : 1);
+    const int total = p_in.NB * p_in.tiles_x * p_in.tiles_y * p_in.tiles_n;
+    // The stream-K hand-over spins on flags written by other CTAs of the same grid: every CTA of the launch must be resident
+    // at once. One CTA (or CTA pair) per SM is what the shared-memory footprint allows; ask the runtime how many it will
+    // really keep resident on this device for this kernel (once per device) and refuse to split when the grid would not fit.
+    static int max_resident[IST_MAX_DEVICES] = {};
+    {
+        const int dev = current_device();
+        if (max_resident[dev] == 0) {
+            int n = 0;
+            cudaLaunchConfig_t qc;
+            memset(&qc, 0, sizeof(qc));
+            qc.gridDim = dim3(num_sms()); qc.blockDim = dim3(HaloCfg<N_TILE, PAIR>::THREADS);
+            qc.dynamicSmemBytes = HaloCfg<N_TILE, PAIR>::SMEM_BYTES;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = PAIR ? 2 : 1; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa; qc.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&n, conv_halo_kernel<N_TILE, PAIR>, &qc) != cudaSuccess || n <= 0) {
+                cudaGetLastError();
+                n = -1;                                  // unknown: trust the one-CTA-per-SM design
+            }
+            max_resident[dev] = n > 0 ? n * (PAIR ? 2 : 1) : -1;
+        }
+    }
+    ConvParams p = p_in;
+    auto grid_of = [&]() {
+        int groups = conv_workers() / p.sk_cpf;        // frame groups that fit side by side
+        if (groups > p.NB) groups = p.NB;
+        if (groups < 1) groups = 1;
+        return groups * p.sk_cpf * (PAIR ? 2 : 1);
+    };
+    int grid = grid_of();
+    if (p.sk_ws != nullptr && max_resident[current_device()] > 0 && grid > max_resident[current_device()]) {
+        // fall back to whole-tile ranges: no CTA waits for another one, so co-residency is not needed (the partition, hence the
+        // rounding, then differs from a device where the split runs — results stay deterministic on this device)
+        const long long tiles_f = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
+        p.sk_ws = nullptr; p.sk_flags = nullptr;
+        p.sk_cpf = tiles_f < conv_workers() ? (int)tiles_f : conv_workers();
+        grid = grid_of();
+    }
     const double px = (double)p.NB * p.H * p.W;
     const int planes = p.passes == 3 ? 2 : 1;
     launch_pre(p.taps == 9 ? (p.mode == CONV_FWD ? "conv_halo_fwd" : "conv_halo_dgrad") : "conv_halo_gram_bwd",
