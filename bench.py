@@ -315,7 +315,7 @@ def run_ours(args):
 
     # ---- batched arm (informational): BATCH independent frames per optimize() call on every GPU (the 256-frame workload of
     # BASELINE configs[3] runs like this); resident inputs, one warm-up batch, one timed batch
-    BATCH = 4
+    BATCH = max(1, args.batch)
     batched = None
     if not args.no_batched:
         cb = torch.cat([frames_dev[i % n_steps] for i in range(BATCH)]).contiguous()
@@ -445,7 +445,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-batched", action="store_true", help="skip the informational 4-frames-per-call measurement")
+    ap.add_argument("--no-batched", action="store_true", help="skip the informational frames-per-call measurement")
+    ap.add_argument("--batch", type=int, default=4, help="frames per optimize() call of the informational batched measurement")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's PyTorch GPU path (N = 1 only, ~25 s)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -6,6 +6,9 @@ The nn.Conv2d sub-modules only hold the parameters (so `.to(device)`, `load_stat
 IST/main.py:25-32); the arithmetic runs in libist_b200.so. Weights are treated as frozen (main.py:31-32): no
 weight-gradient kernel exists, and asking for one raises.
 """
+import collections
+import os
+
 import torch
 import torch.nn as nn
 
@@ -57,7 +60,12 @@ class VGG(nn.Module):
             setattr(self, name, conv)           # registers the parameters under the reference's state-dict keys
         self.forward_seq = list(vcfg.FORWARD_SEQ)
         self.out_seq = list(vcfg.OUT_SEQ)
-        self._plans = {}
+        # Plan cache, least recently used first. A plan pins every activation / gradient buffer of its size (0.35 GB at 512^2,
+        # 5 GB at 2048^2) and, after optimize(), an L-BFGS history (0.63 GB / 10 GB) plus a captured graph; a directory of frames
+        # with many aspect ratios or the 512 -> 1024 -> 2048 schedule would otherwise accumulate them until the device is full
+        # (the reference frees everything per frame). IST_B200_MAX_PLANS overrides the bound.
+        self._plans = collections.OrderedDict()
+        self._max_plans = max(2, int(os.environ.get("IST_B200_MAX_PLANS", "6")))
         self._weights_token = None
 
     # -------------------------------------------------------------------------------------------------------------------
@@ -85,6 +93,10 @@ class VGG(nn.Module):
             plan.weights_token = None
             plan.last_forward_token = None
             self._plans[key] = plan
+            while len(self._plans) > self._max_plans:
+                _, old = self._plans.popitem(last=False)      # least recently used; a later use of it raises (closed handle)
+                old.close()
+        self._plans.move_to_end(key)
         tok = self._token()
         if plan.weights_token != tok:
             plan.load_state_dict(self.state_dict())
@@ -100,7 +112,7 @@ class VGG(nn.Module):
     def release_plans(self):
         for p in self._plans.values():
             p.close()
-        self._plans = {}
+        self._plans = collections.OrderedDict()
 
     def forward(self, input, out_keys):
         if len(self.forward_seq) != len(self.out_seq):

@@ -74,6 +74,8 @@ class Plan:
 
     # ---- forward / features -------------------------------------------------------------------------------------------------
     def _check_x(self, x):
+        if self.h is None:
+            raise _lib.IstError("this plan was closed (evicted from the VGG module's plan cache or released); run VGG.forward again")
         if tuple(x.shape) != (self.batch, 3, self.H, self.W):
             raise _lib.IstError(f"plan is for input {(self.batch, 3, self.H, self.W)}, got {tuple(x.shape)}")
 

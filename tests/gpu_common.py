@@ -43,10 +43,11 @@ def prepare_plan(model, cfg, content, style, batch=None):
     return plan
 
 
-def frames(size, dev, kind="radar", h=None, w=None, cseed=1, sseed=2):
+def frames(size, dev, kind="radar", h=None, w=None, cseed=1, sseed=2, style_kind="lidar"):
     mk = synth.radar_frame if kind == "radar" else synth.smooth_frame
     content = torch.from_numpy(synth.preprocess(mk(size, cseed, h=h, w=w))).to(dev)
-    style = torch.from_numpy(synth.preprocess(synth.lidar_frame(size, sseed, h=h, w=w))).to(dev)
+    mks = synth.lidar_frame if style_kind == "lidar" else synth.smooth_frame
+    style = torch.from_numpy(synth.preprocess(mks(size, sseed, h=h, w=w))).to(dev)
     return content, style
 
 

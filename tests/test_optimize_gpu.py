@@ -70,11 +70,17 @@ def test_eval_counting_matches_reference_loop(model_cfg):
         assert torch.isfinite(x).all()
 
 
-@pytest.mark.parametrize("kind", ["smooth", "radar"])
-def test_optimize_against_oracle(model_cfg, kind):
+@pytest.mark.parametrize("kind,style_kind", [("smooth", "lidar"), ("radar", "lidar"), ("smooth", "smooth")])
+def test_optimize_against_oracle(model_cfg, kind, style_kind):
+    """Free-running 20 evaluations. The pixel-level agreement any two runs of this loop can reach is set by the input class
+    (tools/cpu_trajectory_study.py, profiles/r02_cpu_trajectory_study_128.log: the reference's own fp32-vs-fp64 PSNR after 20
+    evaluations is 36.5 dB for a smooth content + smooth style pair — SURVEY 7.3 H2's 39 dB case —, 17.7 dB for smooth content
+    with the sparse lidar-like style and 22.5 dB for radar + lidar, on the CPU; cuDNN's fp32 path on the GPU sits a few dB lower):
+    the sparse style makes the gradient at x0 rough and the first curvature pairs noise. The gate is therefore relative to the
+    reference's own self-PSNR measured in the same test; the teacher-forced tests pin the arithmetic itself."""
     cfg, model = model_cfg
     size = 128
-    content, style = frames(size, dev, kind)
+    content, style = frames(size, dev, kind, style_kind=style_kind)
     state_np = synth.vgg_state_dict(0, upto="conv5_1")
     st32, st64 = O.state_to_torch(state_np, torch.float32, dev), O.state_to_torch(state_np, torch.float64, dev)
     x = content.clone().requires_grad_(True)
@@ -89,7 +95,7 @@ def test_optimize_against_oracle(model_cfg, kind):
     l_64 = O.loss_and_grad(st64, x64.detach(), t64, full=False)[1]
     l_0 = O.loss_and_grad(st64, content.double(), t64, full=False)[1]
     p_ours, p_floor = psnr(x, x64), psnr(x32, x64)
-    print(f"{kind}: PSNR ours-vs-fp64 {p_ours:.1f} dB, reference fp32-vs-fp64 {p_floor:.1f} dB; "
+    print(f"{kind} content / {style_kind} style: PSNR ours-vs-fp64 {p_ours:.1f} dB, reference fp32-vs-fp64 {p_floor:.1f} dB; "
           f"loss after 20 evals ours {l_ours:.4e} fp32 {l_32:.4e} fp64 {l_64:.4e} (start {l_0:.4e})")
     # same loss level as the reference's own runs, far below the starting loss
     assert l_ours < 0.2 * l_0
