@@ -38,10 +38,30 @@ struct GramCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
 };
 
+// Several layers per launch: the style layers whose features are ready at the same time (relu1_1 ... relu4_1 while conv5_1 is
+// still to run) share ONE grid — blocks [blk_end[l-1], blk_end[l]) work on layer l, longest CTAs (the shallow layers) first —
+// so that the fixed cost of a launch (a wave of ~150 CTAs that live 9-17 us each, then an idle tail) is paid once and the
+// tails of one layer fill with CTAs of the next.
+constexpr int GRAM_MAX_LAYERS = 4;
+struct GramMulti {
+    GramParams L[GRAM_MAX_LAYERS];
+    int blk_end[GRAM_MAX_LAYERS];
+    int n;
+};
+struct alignas(64) GramMaps {
+    CUtensorMap hi[GRAM_MAX_LAYERS];
+    CUtensorMap lo[GRAM_MAX_LAYERS];
+};
+
 __global__ void __launch_bounds__(192, 1)
-gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-                 const GramParams p) {
+gram_syrk_kernel(const __grid_constant__ GramMaps maps, const __grid_constant__ GramMulti mp) {
     using Cfg = GramCfg;
+    int layer = 0;
+    while (layer + 1 < mp.n && (int)blockIdx.x >= mp.blk_end[layer]) ++layer;
+    const GramParams& p = mp.L[layer];
+    const CUtensorMap* tm_hi_p = &maps.hi[layer];
+    const CUtensorMap* tm_lo_p = &maps.lo[layer];
+    const int local = (int)blockIdx.x - (layer > 0 ? mp.blk_end[layer - 1] : 0);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + Cfg::RING_BYTES;
@@ -57,10 +77,14 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    // tile decode: blockIdx.x = split, blockIdx.y = triangular tile id, blockIdx.z = frame
+    // block decode inside the layer: split fastest, then the triangular tile id, then the frame
+    const int tri = p.tiles_c * (p.tiles_c + 1) / 2;
+    const int split = local % p.splits;
+    const int tile_id = (local / p.splits) % tri;
+    const int fr = local / (p.splits * tri);
     int mt = 0, nt = 0;
     {
-        int t = blockIdx.y;
+        int t = tile_id;
         for (int i = 0; i < p.tiles_c; ++i) {
             const int row = p.tiles_c - i;
             if (t < row) { mt = i; nt = i + t; break; }
@@ -68,7 +92,6 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         }
     }
     const bool diag = (mt == nt);
-    const int split = blockIdx.x, fr = blockIdx.z;
     const int total_chunks = (p.HW + 63) >> 6;
     const int c_begin = split * p.chunks_per_split;
     int c_end = c_begin + p.chunks_per_split;
@@ -88,8 +111,8 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
 
     pdl_trigger();
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tm_hi);
-        if (p.passes == 3) tma_prefetch_desc(&tm_lo);
+        tma_prefetch_desc(tm_hi_p);
+        if (p.passes == 3) tma_prefetch_desc(tm_lo_p);
         for (int s = 0; s < Cfg::MAX_STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -120,7 +143,7 @@ gram_syrk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
                 const uint32_t s0 = smem_base + stage * stage_bytes;
                 mbar_arrive_expect_tx(full_bar(stage), tx);
                 for (int pl = 0; pl < planes; ++pl) {
-                    const CUtensorMap* tm = pl == 0 ? &tm_hi : &tm_lo;
+                    const CUtensorMap* tm = pl == 0 ? tm_hi_p : tm_lo_p;
                     for (int g = 0; g < groups_a; ++g)
                         tma_load_3d(s0 + pl * plane_bytes + g * 8192, tm, full_bar(stage), mt * 128 + g * 64, pix, fr);
                     if (!diag)

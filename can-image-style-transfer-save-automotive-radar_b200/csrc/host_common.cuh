@@ -628,29 +628,54 @@ inline void gram_split_plan(int NB, int HW, int C, int* splits, int* chunks_per_
     *chunks_per_split = cps;
     *splits = (total_chunks + cps - 1) / cps;
 }
-inline int launch_gram(cudaStream_t st, const CUtensorMap& m_hi, const CUtensorMap& m_lo, int NB, int HW, int C,
-                       int splits, int chunks_per_split, float* partial, int passes, bool pdl = false) {
+struct GramLaunch {                     // one layer of a Gram launch
+    const CUtensorMap *m_hi, *m_lo;
+    int HW, C, splits, chunks_per_split;
+    float* partial;
+};
+inline int launch_gram_multi(cudaStream_t st, int n, const GramLaunch* layers, int NB, int passes, bool pdl = false) {
     static DeviceOnce attr_once;
     if (attr_once.first()) {
         IST_CUDA(cudaFuncSetAttribute(gram_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg::SMEM_BYTES));
     }
-    if (C % 64 != 0 || (C > 64 && C % 128 != 0)) return fail(IST_ERR_ARG, "gram needs C == 64 or C %% 128 == 0 (got %d)", C);
-    GramParams p;
-    p.NB = NB; p.HW = HW; p.C = C;
-    p.tiles_c = (C + 127) / 128;
-    p.n_tile = C < 128 ? 64 : 128;
-    p.splits = splits;
-    p.chunks_per_split = chunks_per_split;
-    p.passes = passes;
-    p.promote = promote_steps();
-    p.idesc = umma_idesc_f16(UMMA_FMT_F16, 128, p.n_tile, 1, 1);
-    p.partial = partial;
-    const int tri = p.tiles_c * (p.tiles_c + 1) / 2;
-    dim3 grid(splits, tri, NB);
-    launch_pre("gram_syrk", 2.0 * NB * (double)HW * C * C, 4.0 * NB * (double)HW * C + 4.0 * NB * splits * (double)C * C, st);
-    IST_CUDA(launch_k(gram_syrk_kernel, grid, dim3(192), GramCfg::SMEM_BYTES, st, pdl ? PDL_TENSOR : 0, m_hi, m_lo, p));
+    if (n < 1 || n > GRAM_MAX_LAYERS) return fail(IST_ERR_ARG, "gram launch of %d layers (1..%d)", n, GRAM_MAX_LAYERS);
+    GramMaps maps;
+    GramMulti mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.n = n;
+    int blocks = 0;
+    double flops = 0, bytes = 0;
+    for (int l = 0; l < n; ++l) {
+        const GramLaunch& g = layers[l];
+        if (g.C % 64 != 0 || (g.C > 64 && g.C % 128 != 0)) return fail(IST_ERR_ARG, "gram needs C == 64 or C %% 128 == 0 (got %d)", g.C);
+        GramParams& p = mp.L[l];
+        p.NB = NB; p.HW = g.HW; p.C = g.C;
+        p.tiles_c = (g.C + 127) / 128;
+        p.n_tile = g.C < 128 ? 64 : 128;
+        p.splits = g.splits;
+        p.chunks_per_split = g.chunks_per_split;
+        p.passes = passes;
+        p.promote = promote_steps();
+        p.idesc = umma_idesc_f16(UMMA_FMT_F16, 128, p.n_tile, 1, 1);
+        p.partial = g.partial;
+        maps.hi[l] = *g.m_hi;
+        maps.lo[l] = *g.m_lo;
+        const int tri = p.tiles_c * (p.tiles_c + 1) / 2;
+        blocks += g.splits * tri * NB;
+        mp.blk_end[l] = blocks;
+        flops += 2.0 * NB * (double)g.HW * g.C * g.C;
+        bytes += 4.0 * NB * (double)g.HW * g.C + 4.0 * NB * g.splits * (double)g.C * g.C;
+    }
+    for (int l = n; l < GRAM_MAX_LAYERS; ++l) { maps.hi[l] = maps.hi[0]; maps.lo[l] = maps.lo[0]; mp.blk_end[l] = blocks; }
+    launch_pre("gram_syrk", flops, bytes, st);
+    IST_CUDA(launch_k(gram_syrk_kernel, dim3(blocks), dim3(192), GramCfg::SMEM_BYTES, st, pdl ? PDL_TENSOR : 0, maps, mp));
     launch_post(st);
     return IST_OK;
+}
+inline int launch_gram(cudaStream_t st, const CUtensorMap& m_hi, const CUtensorMap& m_lo, int NB, int HW, int C,
+                       int splits, int chunks_per_split, float* partial, int passes, bool pdl = false) {
+    GramLaunch g = {&m_hi, &m_lo, HW, C, splits, chunks_per_split, partial};
+    return launch_gram_multi(st, 1, &g, NB, passes, pdl);
 }
 
 inline int ew_grid(size_t work_items, int block) {

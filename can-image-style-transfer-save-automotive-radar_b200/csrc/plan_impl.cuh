@@ -330,13 +330,24 @@ int run_backward(ist_plan* P, const Seeds& S, int deepest, float* grad, cudaStre
 // Partial sums of the losses whose layer index lies in [lo, hi]: Gram split-K partials of the style layers, squared-error
 // partials of the content layers.
 int run_loss_partials(ist_plan* P, int lo, int hi, cudaStream_t st) {
+    // the Gram partials of all style layers in range share launches of up to GRAM_MAX_LAYERS layers (IST_B200_GRAM_MULTI=0: one
+    // launch per layer)
+    static int multi = -1;
+    if (multi < 0) { const char* e = getenv("IST_B200_GRAM_MULTI"); multi = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
+    GramLaunch gl[GRAM_MAX_LAYERS];
+    int ng = 0;
     for (int k = 0; k < P->n_style; ++k) {
         const int l = P->style_layers[k];
         if (l < lo || l > hi) continue;
         Layer& L = P->layers[l];
         if (!L.target_set) return fail(IST_ERR_STATE, "style target %d not set", k);
-        IST_TRY(run_gram_partial(P, L, st));
+        gl[ng++] = GramLaunch{&L.mGram_hi, &L.mGram_lo, L.H * L.W, L.C, L.splits, L.chunks_per_split, L.gram_partial};
+        if (ng == GRAM_MAX_LAYERS || !multi) {
+            IST_TRY(launch_gram_multi(st, ng, gl, P->NB, P->passes_fwd));
+            ng = 0;
+        }
     }
+    if (ng > 0) IST_TRY(launch_gram_multi(st, ng, gl, P->NB, P->passes_fwd));
     for (int k = 0; k < P->n_content; ++k) {
         const int l = P->content_layers[k];
         if (l < lo || l > hi) continue;
