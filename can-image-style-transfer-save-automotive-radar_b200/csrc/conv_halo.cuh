@@ -259,6 +259,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t a_sbo = halo ? (uint32_t)(Cfg::PW * 128) : 1024u;
     constexpr bool xsingle = Cfg::XSINGLE;
     const uint32_t nmain = (N_TILE == 128) ? (xchunks > 0 ? 2u : 3u) : 4u;       // main accumulation ring (see HaloCfg)
+    // resident-weights mode (see the producer): stages 0 .. 8 hold the nine taps, stages 9 .. B_STAGES-1 are the ring of the fused
+    // Gram k-steps. Only the pair / N = 64 kernel has the stages for it; the host sets the flag for Cin == 64, 9 taps.
+    constexpr int RES_TAPS = 9;
+    constexpr int RES_RING = (Cfg::B_STAGES > RES_TAPS) ? (Cfg::B_STAGES - RES_TAPS) : 1;
+    const bool resident = PAIR && (N_TILE == 64) && (Cfg::B_STAGES > RES_TAPS) && p.b_resident != 0;
 
     // Work distribution ("stream-K" over 64-channel chunks), frame by frame. A tile is CH = cchunks + xchunks chunk units; the
     // Gf = tiles_per_frame * CH units of ONE frame are cut into `cpf` equal contiguous ranges (cpf = CTAs per frame, chosen by
@@ -303,6 +308,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (lane == 0) {
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
+            bool b_loaded = false;
+            int xs = 0;
+            uint32_t xph = 0;
             IST_FOR_SEGMENTS(fr, fcount, tile, cbeg, cend) {
                 (void)fcount;
                 const int tn = tile / tiles_xy;
@@ -330,6 +338,34 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     if (split) tma_load_4d(sA + Cfg::A_PLANE, ex ? &tmF_lo : &tmA_lo, afull(as), c64, x0, y0, fr);
                     }
                     if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
+                    // Resident weights (64 -> 64 layers: ONE 64-channel chunk, so the nine weight tiles of a tile are the same for
+                    // every tile of the launch and fit in nine 8 KB stages): loaded once, never released. Reloading them per tile
+                    // was 72 KB of shared-memory writes per tile in the kernel that is shared-memory-bandwidth bound, and the
+                    // issuers' largest wait. The fused Gram k-step (per-frame D matrix) keeps a ring in the stages behind them.
+                    if (resident) {
+                        if (!ex) {
+                            if (!b_loaded) {
+                                for (int tap = 0; tap < 9; ++tap) {
+                                    const uint32_t sB = b_base + tap * Cfg::B_STAGE;
+                                    const uint32_t lbar = mapa_u32(bfull(tap), 0);
+                                    if (rank == 0) mbar_arrive_expect_tx(bfull(tap), b_tx);
+                                    tma_load_3d_pair(sB, &tmB_hi, lbar, c64, n0, tap);
+                                    if (split) tma_load_3d_pair(sB + Cfg::B_PLANE, &tmB_lo, lbar, c64, n0, tap);
+                                }
+                                b_loaded = true;
+                            }
+                        } else {
+                            const int st = RES_TAPS + xs;
+                            timed_wait(bempty(st), xph ^ 1u, 1);
+                            const uint32_t sB = b_base + st * Cfg::B_STAGE;
+                            const uint32_t lbar = mapa_u32(bfull(st), 0);
+                            if (rank == 0) mbar_arrive_expect_tx(bfull(st), b_tx);
+                            tma_load_3d_pair(sB, &tmD_hi, lbar, c64, n0, fr);
+                            if (split) tma_load_3d_pair(sB + Cfg::B_PLANE, &tmD_lo, lbar, c64, n0, fr);
+                            if (++xs == RES_RING) { xs = 0; xph ^= 1u; }
+                        }
+                        continue;
+                    }
                     const int ntap = ex ? 1 : taps;
                     for (int tap = 0; tap < ntap; ++tap) {
                         const int bz = (p.b_frame || ex) ? fr : tap;
@@ -368,6 +404,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
         uint32_t mb = 0, mph = 0;                  // main ring position and phase
+        int xs1 = 0;                               // resident mode: ring of the fused Gram k-steps' D tiles
+        uint32_t xph1 = 0;
         bool first = true;
         IST_FOR_SEGMENTS(fr, fcount, tile, cbeg, cend) {
             (void)tile; (void)fr; (void)fcount;
@@ -385,23 +423,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         const int in_chain = (ky * kyn + kx) % promote;
                         const bool chain_end = (in_chain == promote - 1) || last_tap;
                         if (in_chain == 0) timed_wait(mempty(mb), mph ^ 1u, 0);
-                        timed_wait(bfull(bs), bph, 1);
+                        const int bstage = resident ? (ky * kyn + kx) : bs;
+                        timed_wait(bfull(bstage), resident ? 0u : bph, 1);      // resident tiles: phase 0 completes once, for good
                         tc_fence_after();
                         if (elect_one()) {
                             const uint32_t d_main = tmem_base + mb * N_TILE;
                             const uint32_t a_lo = a_lo_stage + (uint32_t)((ky * Cfg::PW + kx) * 8);
-                            const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
+                            const uint32_t b_lo = (b_base + bstage * Cfg::B_STAGE) >> 4;
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4)
                                 mma(d_main, a_lo + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, (in_chain | k4) != 0 ? 1u : 0u);
                             if (chain_end) commit(mfull(mb));
-                            commit(bempty(bs));
+                            if (!resident) commit(bempty(bs));
                             if (last_tap) commit(aempty(as));
                         }
                         __syncwarp();
                         first = false;
                         if (chain_end && ++mb == nmain) { mb = 0; mph ^= 1u; }
-                        if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
+                        if (!resident && ++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                     }
                 }
                 if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
@@ -409,14 +448,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             // fused Gram k-steps are issued by warp 6 alone; this warp only keeps the stage rings in step and contributes
             // its share of the release arrivals
             for (int cc = (cbeg > cchunks ? cbeg : cchunks); cc < cend; ++cc) {
+                const int bstage = resident ? RES_TAPS + xs1 : bs;
                 mbar_wait(afull(as), aph);
-                mbar_wait(bfull(bs), bph);
+                mbar_wait(bfull(bstage), resident ? xph1 : bph);
                 if (elect_one()) {
-                    arrive_both(bempty(bs));
+                    arrive_both(bempty(bstage));
                     arrive_both(aempty(as));
                 }
                 __syncwarp();
-                if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
+                if (resident) { if (++xs1 == RES_RING) { xs1 = 0; xph1 ^= 1u; } }
+                else if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                 if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
             }
         }
@@ -432,6 +473,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const int kyn = halo ? 3 : 1;
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
+            int xs2 = 0;
+            uint32_t xph2 = 0;
             uint32_t scount = 0;
             IST_FOR_SEGMENTS(fr, fcount, tile, cbeg, cend) {
                 (void)tile; (void)fr; (void)fcount;
@@ -451,44 +494,47 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                         for (int ky = 0; ky < kyn; ++ky) {
                             for (int kx = 0; kx < kyn; ++kx, ++kit) {
                                 const bool last_tap = (ky == kyn - 1 && kx == kyn - 1);
-                                timed_wait(bfull(bs), bph, 0);
+                                const int bstage = resident ? (ky * kyn + kx) : bs;
+                                timed_wait(bfull(bstage), resident ? 0u : bph, 0);
                                 tc_fence_after();
                                 if (elect_one()) {
                                     const uint32_t a_lo = a_lo_stage + (uint32_t)((ky * Cfg::PW + kx) * 8);
-                                    const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
+                                    const uint32_t b_lo = (b_base + bstage * Cfg::B_STAGE) >> 4;
 #pragma unroll
                                     for (int k4 = 0; k4 < 4; ++k4) {
                                         mma(d_cross, a_lo + 2 * k4, a_hi_w, b_lo + (Cfg::B_PLANE >> 4) + 2 * k4, b_hi_w, idesc,
                                             (kit | k4) != 0 ? 1u : 0u);
                                         mma(d_cross, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc, 1u);
                                     }
-                                    commit(bempty(bs));
+                                    if (!resident) commit(bempty(bs));
                                     if (last_tap) commit(aempty(as));
                                     if (last_tap && last_chunk) commit(xfull(xa));
                                 }
                                 __syncwarp();
-                                if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
+                                if (!resident && ++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                             }
                         }
                     } else {
-                        mbar_wait(bfull(bs), bph);
+                        const int bstage = resident ? RES_TAPS + xs2 : bs;
+                        mbar_wait(bfull(bstage), resident ? xph2 : bph);
                         tc_fence_after();
                         if (elect_one()) {
                             const uint32_t a_lo = a_lo_stage + (uint32_t)((Cfg::PW + 1) * 8);   // centre tap of the halo box
-                            const uint32_t b_lo = (b_base + bs * Cfg::B_STAGE) >> 4;
+                            const uint32_t b_lo = (b_base + bstage * Cfg::B_STAGE) >> 4;
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4) {
                                 mma(d_gram, a_lo + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc2, (xc | k4) != 0 ? 1u : 0u);
                                 mma(d_gram, a_lo + 2 * k4, a_hi_w, b_lo + (Cfg::B_PLANE >> 4) + 2 * k4, b_hi_w, idesc2, 1u);
                                 mma(d_gram, a_lo + (Cfg::A_PLANE >> 4) + 2 * k4, a_hi_w, b_lo + 2 * k4, b_hi_w, idesc2, 1u);
                             }
-                            commit(bempty(bs));
+                            commit(bempty(bstage));
                             commit(aempty(as));
                             if (last_chunk) commit(xfull(xa));
                         }
                         __syncwarp();
                         ++xc;
-                        if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
+                        if (resident) { if (++xs2 == RES_RING) { xs2 = 0; xph2 ^= 1u; } }
+                        else if (++bs == Cfg::B_STAGES) { bs = 0; bph ^= 1u; }
                     }
                     if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
                 }

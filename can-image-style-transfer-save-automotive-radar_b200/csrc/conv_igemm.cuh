@@ -43,6 +43,7 @@ struct ConvParams {
     int passes;          // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi only
     int promote;         // k-steps (of 64 channels) per main accumulation chain, >= 1
     int b_frame;         // 1: third B coordinate is the frame (per-frame B, Gram backward), 0: the tap
+    int b_resident;      // conv_halo pair kernel, Cin == 64, 9 taps: the nine weight tiles stay in shared memory for the whole launch
     int extra_chunks;      // conv_halo: fused Gram-backward k-steps appended to the convolution (0 = none)
     uint32_t idesc2;       // instruction descriptor of those k-steps (fp16 features x fp16 D matrix)
     const float* alpha2_dev;   // [NB] multiplier of the fused Gram accumulator

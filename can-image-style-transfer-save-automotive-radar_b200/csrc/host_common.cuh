@@ -484,6 +484,12 @@ inline int launch_conv(cudaStream_t st, const CUtensorMap& a_hi, const CUtensorM
             p.alpha2_dev = gf->alpha;
         }
         p.dbg_flags = halo_dbg_flags();
+        {
+            // resident weight tiles: pair kernel, N = 64, ONE 64-channel chunk, 3x3 taps (conv1_2 forward and data-gradient)
+            static int res_env = -1;
+            if (res_env < 0) { const char* e = getenv("IST_B200_B_RESIDENT"); res_env = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
+            p.b_resident = (res_env && conv_impl_pair() && nt == 64 && p.Cin == 64 && p.taps == 9 && !p.b_frame && p.passes == 3) ? 1 : 0;
+        }
         if (wsp == nullptr) wsp = &global_conv_workspace();
         IST_TRY(wsp->alloc());
         // stream-K pays (partial-tile exchange, more segments) only when whole-tile waves leave SMs idle: tiles / SMs far from

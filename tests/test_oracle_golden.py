@@ -132,3 +132,68 @@ def test_lbfgs_restatement_matches_torch():
     assert len(tr1) == len(tr2) == 60
     np.testing.assert_allclose(tr1, tr2, rtol=1e-9)
     np.testing.assert_allclose(x1.detach().numpy(), x2.numpy(), rtol=1e-7, atol=1e-9)
+
+
+def test_masked_closure_reproduces_the_plain_closure(state_np):
+    """The flip-aware parity tools (oracle.forward_masks / loss_and_grad_masked, used by the GPU tests to separate mask flips from
+    kernel arithmetic): with the decisions a point takes itself imposed from outside, the closure and its gradient are
+    reproduced exactly, also at x0 = content where every pool window of the constant radar background is an exact tie (first
+    maximum wins, like ATen's max_pool2d backward), and on odd sizes (pool floors)."""
+    state = O.state_to_torch({k: v for k, v in state_np.items() if int(k[4]) <= 5 and not k.startswith(("conv5_2", "conv5_3", "conv5_4"))}, torch.float64)
+    content = torch.from_numpy(synth.preprocess(synth.radar_frame(40, 1, h=37, w=50))).double()
+    style = torch.from_numpy(synth.preprocess(synth.lidar_frame(40, 2, h=37, w=50))).double()
+    targets = O.compute_targets(state, content, style, full=False)
+    gen = torch.Generator().manual_seed(3)
+    for x in (content, content + 20.0 * torch.randn(content.shape, generator=gen, dtype=torch.float64)):
+        ll, tot, g = O.loss_and_grad(state, x, targets, full=False)
+        masks = O.forward_masks(state, x)
+        ll2, tot2, g2 = O.loss_and_grad_masked(state, x, targets, masks)
+        assert tot2 == tot and ll2 == ll and torch.equal(g, g2)
+        mm = O.mask_mismatches(masks, masks)
+        assert all(v[0] == 0 for v in mm.values()) and sum(v[1] for v in mm.values()) > 0
+        assert set(masks) == set(O.OUT_SEQ[:O.OUT_SEQ.index("relu5_1") + 1])
+        assert all(int(masks[k].max()) <= 4 for k in masks if k.startswith("pool"))
+    # a different point takes different decisions, and imposing them changes the gradient
+    m_other = O.forward_masks(state, content + 40.0)
+    assert sum(v[0] for v in O.mask_mismatches(m_other, masks).values()) > 0
+    _, _, g3 = O.loss_and_grad_masked(state, x, targets, m_other)
+    assert not torch.equal(g3, g)
+
+
+def test_lbfgs_restated_log_matches_torch_lbfgs():
+    """LbfgsRestated (the yardstick of the teacher-forced device-optimiser tests) against torch.optim.LBFGS on a small non-convex
+    problem in float64: same iterates, and its per-iteration log (direction, step, accepted pair, history length) is consistent
+    with them — across the eviction of a 5-pair ring and a rejected pair."""
+    gen = torch.Generator().manual_seed(0)
+    n = 300
+    a = torch.exp(torch.empty(n, dtype=torch.float64).uniform_(-3.0, -1.0, generator=gen))
+    b = torch.empty(n, dtype=torch.float64).uniform_(-3, 3, generator=gen)
+    c = 4.0 * torch.rand(n, dtype=torch.float64, generator=gen)
+    x0 = torch.empty(n, dtype=torch.float64).uniform_(-3, 3, generator=gen)
+
+    def f(x):
+        return (0.5 * a * (x - b) ** 2 + c * torch.cos(x)).sum()
+    xt = x0.clone().requires_grad_(True)
+    topt = torch.optim.LBFGS([xt], history_size=5)
+    xr = x0.clone()
+    ropt = O.LbfgsRestated(history_size=5)
+    ropt.log = []
+    for _ in range(3):
+        def closure_t():
+            topt.zero_grad()
+            loss = f(xt)
+            loss.backward()
+            return loss
+        topt.step(closure_t)
+
+        def closure_r():
+            xx = xr.clone().requires_grad_(True)
+            loss = f(xx)
+            loss.backward()
+            return float(loss), xx.grad.detach()
+        ropt.step(xr, closure_r)
+        assert torch.allclose(xt.detach(), xr, rtol=1e-9, atol=1e-9)
+    assert ropt.state["func_evals"] == topt.state[topt._params[0]]["func_evals"]
+    assert max(e["hist"] for e in ropt.log) == 5
+    assert any(e["n_iter"] > 1 and not e["accepted"] for e in ropt.log), "the scenario contains a rejected curvature pair"
+    assert all(e["applied"] for e in ropt.log)
