@@ -94,6 +94,9 @@ struct ist_plan {
 
 namespace {
 
+// side-stream overlap of the loss partials (IST_B200_NO_OVERLAP=1 / ist_set_option("overlap", 0) turn it off): -1 = undecided
+int& overlap_flag() { static int v = -1; return v; }
+
 int check_device() {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -425,6 +428,7 @@ int ist_set_option(const char* name, int value) {
     if (name == nullptr) return fail(IST_ERR_ARG, "ist_set_option: null name");
     if (strcmp(name, "first_conv_fwd_tc") == 0) { cff_flag() = value != 0 ? 1 : 0; return IST_OK; }
     if (strcmp(name, "first_conv_dgrad_tc") == 0) { cfd_flag() = value != 0 ? 1 : 0; return IST_OK; }
+    if (strcmp(name, "overlap") == 0) { overlap_flag() = value != 0 ? 1 : 0; return IST_OK; }
     return fail(IST_ERR_ARG, "ist_set_option: unknown option '%s'", name);
 }
 
@@ -727,7 +731,7 @@ int ist_plan_loss_and_grad(ist_plan* P, const float* x_dev, float* grad_dev, flo
     if (deepest < 0) return fail(IST_ERR_STATE, "no loss configured (ist_plan_set_loss)");
     cudaStream_t st = (cudaStream_t)stream;
     for (Layer& L : P->layers) L.ext_active = false;
-    static int overlap_env = -1;
+    int& overlap_env = overlap_flag();
     if (overlap_env < 0) { const char* e = getenv("IST_B200_NO_OVERLAP"); overlap_env = (e != nullptr && atoi(e) == 1) ? 0 : 1; }
     if (overlap_env && deepest >= 2 && P->side != nullptr) {
         // everything up to the layer before the deepest one, then fork: the loss partials of the shallower layers run on the

@@ -50,7 +50,9 @@ int ist_device_check(void);
 
 /* run-time kernel selection for the conv1_1 kernels (same effect as the IST_B200_CFF / IST_B200_CFD environment variables,
  * but switchable inside one process so that the parity tests cover both variants): "first_conv_fwd_tc",
- * "first_conv_dgrad_tc": 1 = tensor-core kernel (default), 0 = CUDA-core kernel. Applies to plans and per-op entry points. */
+ * "first_conv_dgrad_tc": 1 = tensor-core kernel (default), 0 = CUDA-core kernel. Applies to plans and per-op entry points.
+ * "overlap": 1 = the loss partials of the shallow style layers run on a side stream next to the deepest conv (default),
+ * 0 = everything on the caller's stream (per-launch profiling: a kernel's event time is then its own). */
 int ist_set_option(const char* name, int value);
 
 /* kernels launched by this library in this process so far (kernels inside a replayed CUDA graph are counted per replay) */
