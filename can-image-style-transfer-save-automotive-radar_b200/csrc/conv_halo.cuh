@@ -410,7 +410,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         IST_FOR_SEGMENTS(fr, fcount, tile, cbeg, cend) {
             (void)tile; (void)fr; (void)fcount;
             const int mend = cend < cchunks ? cend : cchunks;          // main chunks of the segment: [cbeg, mend)
-            const int kit_seg = (mend > cbeg ? mend - cbeg : 0) * taps;
             int kit = 0;
             for (int cc = cbeg; cc < mend; ++cc) {
                 timed_wait(afull(as), aph, 2);
