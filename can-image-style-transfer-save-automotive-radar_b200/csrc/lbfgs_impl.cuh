@@ -686,11 +686,22 @@ lbfgs_update_kernel(const LbParams P) {
                     lb_store8(P.Y + ho, base, n_left, lane, vec, yv);
                 }
             }
+            // the loads of pair i + 1 are issued before the (long, dependent) compensated sums of pair i
+            float s_n[8], y_n[8];
+            if (nread > 0) {
+                const size_t h0 = ((size_t)s_slot[0] * P.NB + b) * (size_t)n;
+                lb_load8(P.S + h0, base, n_left, lane, vec, s_n);
+                lb_load8(P.Y + h0, base, n_left, lane, vec, y_n);
+            }
             for (int i = 0; i < nread; ++i) {
-                const size_t ho = ((size_t)s_slot[i] * P.NB + b) * (size_t)n;
                 float s_i[8], y_i[8];
-                lb_load8(P.S + ho, base, n_left, lane, vec, s_i);
-                lb_load8(P.Y + ho, base, n_left, lane, vec, y_i);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { s_i[e] = s_n[e]; y_i[e] = y_n[e]; }
+                if (i + 1 < nread) {
+                    const size_t ho = ((size_t)s_slot[i + 1] * P.NB + b) * (size_t)n;
+                    lb_load8(P.S + ho, base, n_left, lane, vec, s_n);
+                    lb_load8(P.Y + ho, base, n_left, lane, vec, y_n);
+                }
                 const float cyh = s_cyh[i], cyl = s_cyl[i], csh = s_csh[i], csl = s_csl[i];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
