@@ -12,7 +12,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("env", [{"IST_B200_CONV": "halo"}, {"IST_B200_CONV": "pair", "IST_B200_PROMOTE_FWD": "1"},
-                                 {"IST_B200_NO_STREAMK": "1"}, {"IST_B200_NO_PDL": "1"}, {"IST_B200_CFD": "cuda", "IST_B200_CFF": "cuda"}])
+                                 {"IST_B200_NO_STREAMK": "1"}, {"IST_B200_NO_PDL": "1"}, {"IST_B200_CFD": "cuda", "IST_B200_CFF": "cuda"},
+                                 # round 2 switches: weight tiles reloaded per tile, one Gram launch per layer, no side stream
+                                 {"IST_B200_B_RESIDENT": "0", "IST_B200_GRAM_MULTI": "0", "IST_B200_NO_OVERLAP": "1"}])
 def test_closure_parity_in_other_configurations(env):
     e = dict(os.environ)
     e.update(env)
