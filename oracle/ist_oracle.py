@@ -1,7 +1,8 @@
 """CPU/PyTorch restatement of the reference's Gatys style-transfer path — TEST INFRASTRUCTURE ONLY.
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may import this module, and
-only as the checker or the timed baseline — never as the product path (the product path is the CUDA library behind
+Only tests/, __graft_entry__.smoke() and bench.py's baseline legs (cpu_baseline, `--impl reference`, and `gpu_reference`: the
+reference's own PyTorch GPU path timed beside the product on the same B200) may import this module, and only as the checker
+or the timed baseline — never as the product path (the product path is the CUDA library behind
 include/ist_b200.h and raises when that library is missing).
 
 What is restated (paths relative to the reference root, DJNing/Can-Image-Style-Transfer-Save-Automotive-Radar):
