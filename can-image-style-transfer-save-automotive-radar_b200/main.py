@@ -89,6 +89,8 @@ def main(argv=None):
     parser.add_argument("--prefetch", type=int, default=2, help="batches decoded and uploaded ahead of the GPU")
     parser.add_argument("--skip-existing", action="store_true", help="do not recompute frames whose output file exists")
     parser.add_argument("--no-gather", action="store_true", help="skip the end-of-run gather of the finished frames (files only)")
+    parser.add_argument("--gather-limit-mb", type=int, default=4096,
+                        help="skip the gather (files only) when the finished 8-bit frames of the whole job exceed this many MiB")
     parser.add_argument("--summary-json", default="", help="rank 0 writes a one-line JSON summary (frames/s incl. I/O) here")
     parser.add_argument("opts", help="Modify config options using the command-line", default=None, nargs=argparse.REMAINDER)
     args = parser.parse_args(argv)
@@ -117,6 +119,10 @@ def main(argv=None):
     if args.max_frames > 0:
         frames = frames[: args.max_frames]
     mine = shard_indices(len(frames), rank, world)
+    # the gathered batch lives on every GPU: the same decision on every rank, from the job size alone
+    job_mib = len(frames) * 3 * int(cfg.DATA.IMG_SIZE) ** 2 * 2 / 2 ** 20          # x2: Scale keeps the aspect ratio (non-square frames)
+    if job_mib > args.gather_limit_mb:
+        args.no_gather = True
 
     if args.high_resolution:
         # the coarse-to-fine second stage re-reads the content image at HRDATA.IMG_SIZE: plain per-frame loop (main.py:59-75)
