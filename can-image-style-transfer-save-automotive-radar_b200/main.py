@@ -139,7 +139,7 @@ def main(argv=None):
         results, stats = {}, {"frames": len(done), "skipped": len(mine) - len(done)}
     else:
         pipe = FramePipeline(cfg, model, device, style_image, cfg.OUTPUT.DIR, frames_per_batch=args.frames_per_batch,
-                             prefetch=args.prefetch, keep_results=(world > 1 and not args.no_gather) or bool(args.summary_json))
+                             prefetch=args.prefetch, keep_results=(not args.no_gather) and (world > 1 or bool(args.summary_json)))
         done = pipe.run(frames, mine, skip_existing=args.skip_existing)
         pipe.close()
         results, stats = pipe.results, dict(pipe.stats)
