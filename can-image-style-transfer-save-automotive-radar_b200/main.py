@@ -84,7 +84,7 @@ def main(argv=None):
     parser.add_argument("--output-dir", default="./output/full_transfer/", help="where the stylised frames go")
     parser.add_argument("--max-frames", type=int, default=0, help="process at most this many frames (0 = all)")
     parser.add_argument("--high-resolution", action="store_true", help="run the coarse-to-fine second stage (serial per frame)")
-    parser.add_argument("--frames-per-batch", type=int, default=1,
+    parser.add_argument("--frames-per-batch", type=int, default=4,
                         help="optimise this many (independent, equally sized) frames side by side on each GPU")
     parser.add_argument("--prefetch", type=int, default=2, help="batches decoded and uploaded ahead of the GPU")
     parser.add_argument("--skip-existing", action="store_true", help="do not recompute frames whose output file exists")
